@@ -1,0 +1,76 @@
+"""ctypes binding of libb21.so (the C-ABI declared in include/b21.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+PyTorch is only used for device memory and streams; every signature is plain pointers and integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libb21.so"
+STAT_SLOTS = 32
+
+_vp, _i, _f, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
+
+# name -> argtypes (all functions return int status unless listed in _SPECIAL)
+_SIGNATURES = {
+    "b21_conv_cout_padded": [_i],
+    "b21_pack_conv_weight": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b21_conv3d_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every symbol include/b21.h declares (used by the CPU-side ABI test)."""
+    return ["b21_last_error", "b21_version", *_SIGNATURES.keys()]
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if os.environ.get("B21_AUTOBUILD", "1") == "1":
+            from .build import build_lib
+            build_lib()
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.b21_last_error.restype = C.c_char_p
+    lib.b21_last_error.argtypes = []
+    lib.b21_version.restype = _i
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _i
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().b21_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libb21 {what} failed ({status}): {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)
