@@ -22,6 +22,16 @@ _SIGNATURES = {
     "b21_conv_cout_padded": [_i],
     "b21_pack_conv_weight": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b21_conv3d_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _vp],
+    "b21_se_gate": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    "b21_scale_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_upsample2x": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_upsample_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b21_head_conv": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "b21_pack_windows": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b21_blend_accumulate": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b21_tta_accumulate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp],
+    "b21_labels_finalize": [_vp, _f, _f, _vp, _i, _vp, _vp, _i64, _i, _vp],
 }
 
 _lib = None

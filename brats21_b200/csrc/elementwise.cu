@@ -1,0 +1,437 @@
+// elementwise.cu — HBM-bound kernels of the network body on channels-last (NDHWC) bf16 activations.
+// Every kernel moves 16-byte vectors (8 channels), keeps consecutive lanes on consecutive addresses, holds
+// per-channel parameters in registers/shared memory and sizes its grid as a multiple of the SM count.
+//
+//   norm_apply   GroupNorm(8,C)+ReLU (networks/factory.py:182, equiunet2020.py:60-61) or EvoNorm3D-S0
+//                (networks/equiunet2021.py:48-52,95-105) from the (sum, sumsq) group statistics the conv epilogue
+//                produced; optional per-channel output sums for the squeeze-excite mean.
+//   se_gate      MONAI ResidualSELayer MLP -> per (n, c) scale 1 + sigmoid(...)   (equiunet2021.py:204-205)
+//   scale_pool   x * scale written full-res and/or 2x2x2 max / [max, avg] pooled  (MaxPool3d equiunet2020.py:433,
+//                MONAI MaxAvgPool equiunet2021.py:261)
+//   upsample2x   trilinear x2, align_corners=True, into a channel slice           (equiunet2020.py:439)
+//   head_conv    1x1 conv C -> K<=4 logits, NCDHW fp32 out                         (equiunet2020.py:441, 2021.py:271)
+//   upsample_f32 trilinear xS (align_corners) on NCDHW fp32 (deep-supervision heads, equiunet2021.py:274-280)
+#include "ptx.cuh"
+#include "host_common.h"
+
+namespace b21 {
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------ norm apply
+// grid = (gx, N) with gx * blockDim a multiple of C/8, so that each thread always serves the same 8 channels.
+template <int MODE>  // 0 = GroupNorm+ReLU, 1 = EvoNorm-S0
+__global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x, int ldx,  // x may alias y
+                                                         __nv_bfloat16* y, int ldy,
+                                                         const double* __restrict__ stats,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* chan_sum, int N,
+                                                         long long nvox, int C, float eps) {
+  extern __shared__ float sm[];  // a[C], b[C], csum[C]
+  float* sa = sm;
+  float* sb = sm + C;
+  float* ssum = sm + 2 * C;
+  const int n = blockIdx.y;
+  const int gsz = C / 8;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gsz;
+    double s = 0.0, q = 0.0;
+    for (int slot = 0; slot < B21_STAT_SLOTS; ++slot) {
+      const double* p = stats + ((size_t(slot) * N + n) * 8 + g) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    const double cnt = double(nvox) * gsz;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (MODE == 0) {
+      const float rstd = float(1.0 / sqrt(var + double(eps)));
+      sa[c] = gamma[c] * rstd;
+      sb[c] = beta[c] - float(mean) * gamma[c] * rstd;
+    } else {
+      const double varu = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;  // torch.var default: unbiased
+      sa[c] = gamma[c] * float(1.0 / sqrt(varu + double(eps)));
+      sb[c] = beta[c];
+    }
+    ssum[c] = 0.f;
+  }
+  __syncthreads();
+  const int chunks = C >> 3;
+  const long long total = nvox * chunks;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ck = int(i % chunks);  // invariant: T % chunks == 0
+  float a[8], b[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = sa[ck * 8 + j];
+    b[j] = sb[ck * 8 + j];
+    acc[j] = 0.f;
+  }
+  const __nv_bfloat16* xn = x + size_t(n) * nvox * ldx;
+  __nv_bfloat16* yn = y + size_t(n) * nvox * ldy;
+  constexpr int U = 4;
+  for (; i < total; i += T * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * T;
+      if (iu < total) v[u] = *reinterpret_cast<const uint4*>(xn + (iu / chunks) * ldx + ck * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * T;
+      if (iu < total) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float r;
+          if (MODE == 0) {
+            r = fmaxf(fmaf(f[j], a[j], b[j]), 0.f);
+          } else {
+            const float sw = __fdividef(f[j], 1.f + __expf(-f[j]));  // x * sigmoid(x)
+            r = fmaf(sw, a[j], b[j]);
+          }
+          f[j] = r;
+        }
+        const uint4 o = pack8(f);
+        if (chan_sum) {  // sums of the ROUNDED outputs: what the next layer actually sees
+          float g[8];
+          unpack8(o, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += g[j];
+        }
+        *reinterpret_cast<uint4*>(yn + (iu / chunks) * ldy + ck * 8) = o;
+      }
+    }
+  }
+  if (chan_sum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&ssum[ck * 8 + j], acc[j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + size_t(n) * C + c, ssum[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ SE gate
+// one block per n: scale[n][c] = 1 + sigmoid(W2 relu(W1 m + b1) + b2), m = chan_sum * inv_count
+__global__ void se_gate_kernel(const float* __restrict__ chan_sum, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2,
+                               const float* __restrict__ b2, float* __restrict__ scale, int C, int Hd,
+                               float inv_count) {
+  extern __shared__ float sm[];  // m[C], hid[Hd]
+  float* m = sm;
+  float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m[c] = chan_sum[size_t(n) * C + c] * inv_count;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < Hd; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w1[size_t(j) * C + c] * m[c];
+    s = warp_sum(s);
+    if (lane == 0) hid[j] = fmaxf(s + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nw) {
+    float s = 0.f;
+    for (int j = lane; j < Hd; j += 32) s += w2[size_t(c) * Hd + j] * hid[j];
+    s = warp_sum(s);
+    if (lane == 0) scale[size_t(n) * C + c] = 1.f + 1.f / (1.f + expf(-(s + b2[c])));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ scale + pool
+// One thread per (pooled voxel, 8-channel chunk): reads the 2x2x2 block, optionally writes it back scaled
+// (full-res, may alias x) and writes max (mode 1) or [max | avg] (mode 2) at half resolution.
+__global__ void __launch_bounds__(256) scale_pool_kernel(const __nv_bfloat16* x, int ldx,
+                                                         const float* __restrict__ scale, __nv_bfloat16* full,
+                                                         int ldfull, __nv_bfloat16* __restrict__ pooled, int ldpool,
+                                                         int mode, int N, int D, int H, int W, int C) {
+  const int chunks = C >> 3;
+  const int Dp = D >> 1, Hp = H >> 1, Wp = W >> 1;
+  const long long total = (long long)N * Dp * Hp * Wp * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ck = int(i % chunks);
+    long long v = i / chunks;
+    const int wp = int(v % Wp); v /= Wp;
+    const int hp = int(v % Hp); v /= Hp;
+    const int dp = int(v % Dp);
+    const int n = int(v / Dp);
+    float sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = scale ? __ldg(scale + size_t(n) * C + ck * 8 + j) : 1.f;
+    float mx[8], sm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mx[j] = -INFINITY; sm[j] = 0.f; }
+    uint4 raw[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const size_t vox = ((size_t(n) * D + (2 * dp + (t >> 2))) * H + (2 * hp + ((t >> 1) & 1))) * W + (2 * wp + (t & 1));
+      raw[t] = *reinterpret_cast<const uint4*>(x + vox * ldx + ck * 8);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float f[8];
+      unpack8(raw[t], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= sc[j];
+      uint4 o = pack8(f);
+      if (full) {
+        const size_t vox = ((size_t(n) * D + (2 * dp + (t >> 2))) * H + (2 * hp + ((t >> 1) & 1))) * W + (2 * wp + (t & 1));
+        *reinterpret_cast<uint4*>(full + vox * ldfull + ck * 8) = o;
+      }
+      unpack8(o, f);  // pool what downstream layers see (bf16-rounded)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { mx[j] = fmaxf(mx[j], f[j]); sm[j] += f[j]; }
+    }
+    if (pooled) {
+      const size_t pv = ((size_t(n) * Dp + dp) * Hp + hp) * Wp + wp;
+      *reinterpret_cast<uint4*>(pooled + pv * ldpool + ck * 8) = pack8(mx);
+      if (mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[j] *= 0.125f;
+        *reinterpret_cast<uint4*>(pooled + pv * ldpool + C + ck * 8) = pack8(sm);
+      }
+    }
+  }
+}
+
+// scale only (no pooling): y = x * scale[n][c]
+__global__ void __launch_bounds__(256) scale_kernel(const __nv_bfloat16* x, int ldx, const float* __restrict__ scale,
+                                                    __nv_bfloat16* y, int ldy, int N, long long nvox, int C) {
+  const int chunks = C >> 3;
+  const long long total = (long long)N * nvox * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ck = int(i % chunks);
+    const long long v = i / chunks;
+    const int n = int(v / nvox);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + v * ldx + ck * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= __ldg(scale + size_t(n) * C + ck * 8 + j);
+    *reinterpret_cast<uint4*>(y + v * ldy + ck * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ trilinear x2
+__device__ __forceinline__ void lerp_setup(int o, int I, int O, int& i0, int& i1, float& l1) {
+  // torch upsample, align_corners=True: src = o * (I-1)/(O-1)
+  const float sc = (O > 1) ? float(I - 1) / float(O - 1) : 0.f;
+  const float src = sc * float(o);
+  i0 = int(src);
+  if (i0 > I - 1) i0 = I - 1;
+  i1 = i0 + (i0 < I - 1 ? 1 : 0);
+  l1 = src - float(i0);
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                         __nv_bfloat16* __restrict__ y, int ldy, int N, int D, int H,
+                                                         int W, int C) {
+  const int chunks = C >> 3;
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * Do * Ho * Wo * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ck = int(i % chunks);
+    long long v = i / chunks;
+    const int wo = int(v % Wo); v /= Wo;
+    const int ho = int(v % Ho); v /= Ho;
+    const int d_o = int(v % Do);
+    const int n = int(v / Do);
+    int d0, d1, h0, h1, w0, w1;
+    float ld, lh, lw;
+    lerp_setup(d_o, D, Do, d0, d1, ld);
+    lerp_setup(ho, H, Ho, h0, h1, lh);
+    lerp_setup(wo, W, Wo, w0, w1, lw);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int dd = (t & 4) ? d1 : d0, hh = (t & 2) ? h1 : h0, ww = (t & 1) ? w1 : w0;
+      const float wt = ((t & 4) ? ld : 1.f - ld) * ((t & 2) ? lh : 1.f - lh) * ((t & 1) ? lw : 1.f - lw);
+      const size_t vox = ((size_t(n) * D + dd) * H + hh) * W + ww;
+      float f[8];
+      unpack8(ldg16(x + vox * ldx + ck * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, f[j], acc[j]);
+    }
+    const size_t ov = ((size_t(n) * Do + d_o) * Ho + ho) * Wo + wo;
+    *reinterpret_cast<uint4*>(y + ov * ldy + ck * 8) = pack8(acc);
+  }
+}
+
+// trilinear xS on NCDHW fp32 planes (deep-supervision heads): one thread per output element
+__global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           int planes, int D, int H, int W, int S) {
+  const int Do = S * D, Ho = S * H, Wo = S * W;
+  const long long total = (long long)planes * Do * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long v = i;
+    const int wo = int(v % Wo); v /= Wo;
+    const int ho = int(v % Ho); v /= Ho;
+    const int d_o = int(v % Do);
+    const int pl = int(v / Do);
+    int d0, d1, h0, h1, w0, w1;
+    float ld, lh, lw;
+    lerp_setup(d_o, D, Do, d0, d1, ld);
+    lerp_setup(ho, H, Ho, h0, h1, lh);
+    lerp_setup(wo, W, Wo, w0, w1, lw);
+    const float* xp = x + size_t(pl) * D * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int dd = (t & 4) ? d1 : d0, hh = (t & 2) ? h1 : h0, ww = (t & 1) ? w1 : w0;
+      const float wt = ((t & 4) ? ld : 1.f - ld) * ((t & 2) ? lh : 1.f - lh) * ((t & 1) ? lw : 1.f - lw);
+      acc = fmaf(wt, __ldg(xp + (size_t(dd) * H + hh) * W + ww), acc);
+    }
+    y[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 1x1 head conv
+// logits[n][k][vox] = b[k] + sum_c w[k][c] * scale[n][c] * x[n][vox][c];  K <= 4, C <= 512
+template <int K>
+__global__ void __launch_bounds__(256) head_conv_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float* __restrict__ out, int N, long long nvox, int C) {
+  extern __shared__ float sw[];  // [K][C] (pre-scaled per n)
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x)
+    sw[i] = w[i] * (scale ? scale[size_t(n) * C + (i % C)] : 1.f);
+  __syncthreads();
+  const __nv_bfloat16* xn = x + size_t(n) * nvox * ldx;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox;
+       v += (long long)gridDim.x * blockDim.x) {
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = b ? __ldg(b + k) : 0.f;
+    const __nv_bfloat16* xv = xn + v * ldx;
+    for (int c = 0; c < C; c += 8) {
+      float f[8];
+      unpack8(ldg16(xv + c), f);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], sw[k * C + c + j], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[(size_t(n) * K + k) * nvox + v] = acc[k];
+  }
+}
+
+static inline int grid_for(long long work_items, int threads, int multiple_of = 1) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  blocks = (blocks + multiple_of - 1) / multiple_of * multiple_of;
+  return int(blocks);
+}
+
+}  // namespace b21
+
+using namespace b21;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const double* stats, const float* gamma,
+                              const float* beta, float* chan_sum, int mode, int n, long long nvox, int c, float eps,
+                              void* stream) {
+  B21_CHECK_ARG(x && y && stats && gamma && beta, "norm_apply: null pointer");
+  B21_CHECK_ARG(mode == 0 || mode == 1, "norm_apply: mode must be 0 (GN+ReLU) or 1 (EvoNorm-S0)");
+  B21_CHECK_ARG(c % 8 == 0 && (c / 8) >= 1 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= c && ldy >= c, "norm_apply: bad C/ld");
+  B21_CHECK_ARG(n > 0 && nvox > 0, "norm_apply: empty tensor");
+  const int chunks = c / 8;
+  long long blocks = (nvox * chunks + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (long long)num_sms() * 8 / n > 0 ? (long long)num_sms() * 8 / n : 1;
+  if (blocks > cap) blocks = cap;
+  const int gx = int((blocks + chunks - 1) / chunks * chunks);  // gx*256 must be a multiple of C/8
+  const size_t smem = sizeof(float) * 3 * c;
+  dim3 grid(gx, n);
+  if (mode == 0)
+    norm_apply_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, n, nvox, c, eps);
+  else
+    norm_apply_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, n, nvox, c, eps);
+  B21_LAUNCH_CHECK("norm_apply_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_se_gate(const float* chan_sum, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* scale, int n, int c, int hidden, float inv_count, void* stream) {
+  B21_CHECK_ARG(chan_sum && w1 && b1 && w2 && b2 && scale, "se_gate: null pointer");
+  B21_CHECK_ARG(n > 0 && c > 0 && hidden > 0, "se_gate: bad sizes");
+  se_gate_kernel<<<n, 256, sizeof(float) * (c + hidden), (cudaStream_t)stream>>>(chan_sum, w1, b1, w2, b2, scale, c, hidden, inv_count);
+  B21_LAUNCH_CHECK("se_gate_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_scale_pool(const void* x, int ldx, const float* scale, void* full, int ldfull, void* pooled,
+                              int ldpool, int mode, int n, int d, int h, int w, int c, void* stream) {
+  B21_CHECK_ARG(x, "scale_pool: null input");
+  B21_CHECK_ARG(c % 8 == 0 && ldx % 8 == 0, "scale_pool: C/ld must be multiples of 8");
+  B21_CHECK_ARG(mode >= 0 && mode <= 2, "scale_pool: mode 0 (scale only), 1 (max), 2 (max|avg)");
+  if (mode == 0) {
+    B21_CHECK_ARG(scale && full, "scale_pool: mode 0 needs scale and full");
+    const long long nvox = (long long)d * h * w;
+    scale_kernel<<<grid_for((long long)n * nvox * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, scale, (bf16*)full, ldfull, n, nvox, c);
+    B21_LAUNCH_CHECK("scale_kernel");
+    return B21_OK;
+  }
+  B21_CHECK_ARG(pooled && d % 2 == 0 && h % 2 == 0 && w % 2 == 0, "scale_pool: pooling needs even dims and an output");
+  B21_CHECK_ARG(ldpool % 8 == 0 && ldpool >= (mode == 2 ? 2 * c : c), "scale_pool: pooled ld too small");
+  const long long items = (long long)n * (d / 2) * (h / 2) * (w / 2) * (c / 8);
+  scale_pool_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, scale, (bf16*)full, ldfull, (bf16*)pooled, ldpool, mode, n, d, h, w, c);
+  B21_LAUNCH_CHECK("scale_pool_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_upsample2x(const void* x, int ldx, void* y, int ldy, int n, int d, int h, int w, int c,
+                              void* stream) {
+  B21_CHECK_ARG(x && y && c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x: bad args");
+  const long long items = (long long)n * d * h * w * 8 * (c / 8);
+  upsample2x_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, n, d, h, w, c);
+  B21_LAUNCH_CHECK("upsample2x_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_upsample_f32(const float* x, float* y, int planes, int d, int h, int w, int s, void* stream) {
+  B21_CHECK_ARG(x && y && planes > 0 && s >= 1, "upsample_f32: bad args");
+  const long long items = (long long)planes * d * h * w * s * s * s;
+  upsample_f32_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(x, y, planes, d, h, w, s);
+  B21_LAUNCH_CHECK("upsample_f32_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_head_conv(const void* x, int ldx, const float* scale, const float* w, const float* b, float* out,
+                             int n, long long nvox, int c, int k, void* stream) {
+  B21_CHECK_ARG(x && w && out, "head_conv: null pointer");
+  B21_CHECK_ARG(k >= 1 && k <= 4 && c % 8 == 0 && c <= 1024, "head_conv: K must be 1..4 and C a multiple of 8");
+  dim3 grid(grid_for(nvox, 256), n);
+  const size_t smem = sizeof(float) * k * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k) {
+    case 1: head_conv_kernel<1><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
+    case 2: head_conv_kernel<2><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
+    case 3: head_conv_kernel<3><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
+    default: head_conv_kernel<4><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
+  }
+  B21_LAUNCH_CHECK("head_conv_kernel");
+  return B21_OK;
+}

@@ -1,0 +1,73 @@
+"""Factories with the reference's names and argument meaning (src/definer.py): ``get_model(args)`` keyed on
+``args.model`` with ``args.width / norm / act / dropout / num_classes``; ``get_tta_transforms()``;
+``get_activation()``; ``get_post_transforms(args)``; ``make_criterion(args)``; ``make_optimizer(args, model)``.
+``get_network`` is an alias of ``get_model`` (the name BASELINE.json uses)."""
+from __future__ import annotations
+
+import argparse
+
+import torch
+
+from . import tta as _tta
+from .networks import EquiUnet, EquiUnetASSPEvo
+
+_SUPPORTED = {
+    "equiunet": EquiUnet,
+    "equiunet_assp_evo": EquiUnetASSPEvo,
+    "equiunet_assp_evocor": EquiUnetASSPEvo,  # same network, renamed in the reference's docker configs
+}
+
+
+def get_model(args: argparse.Namespace) -> torch.nn.Module:
+    """src/definer.py:37-174 for the model families on the accelerated path; NameError otherwise (as the
+    reference does for unknown names)."""
+    if args.model not in _SUPPORTED:
+        raise NameError("Not Supported Model")
+    kwargs = {"inplanes": 4,
+              "num_classes": args.num_classes,
+              "features": [args.width * 2 ** i for i in range(4)],
+              "norm_layer": getattr(args, "norm", "group"),
+              "act": getattr(args, "act", "relu"),
+              "deep_supervision": True,  # hard-coded in the reference (definer.py:140)
+              "dropout": getattr(args, "dropout", 0)}
+    return _SUPPORTED[args.model](**kwargs)
+
+
+get_network = get_model
+
+
+def get_tta_transforms() -> _tta.Compose:
+    return _tta.get_tta_transforms()
+
+
+def get_activation():
+    """monai Activations(sigmoid=True) (definer.py:661-668)."""
+    return torch.sigmoid
+
+
+def get_post_transforms(args: argparse.Namespace):
+    """AsDiscrete(threshold_values=True, logit_thresh=...) (definer.py:671-697); the label-cleaning options
+    (connected components / closest-value replacement) are CPU graph algorithms outside the hot path."""
+    if getattr(args, "replace_value", False) or getattr(args, "cleaning_areas", False):
+        raise NotImplementedError("connected-component cleaning / value replacement are out of scope (SURVEY §8f)")
+    thresh = getattr(args, "logit_threshold", 0.5)
+    return lambda x: (x >= thresh).float()
+
+
+def make_criterion(args: argparse.Namespace):
+    from .losses import DiceLoss
+    if args.criterion == "dice":
+        return DiceLoss(jaccard=False)
+    if args.criterion == "jaccard":
+        return DiceLoss(jaccard=True)
+    raise NameError("Not Supported Criterion")
+
+
+def make_optimizer(args: argparse.Namespace, model: torch.nn.Module):
+    from .optimizer import Ranger2020
+    if args.optimizer != "ranger":
+        raise NameError("Not Supported Optimizer")
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    return Ranger2020(trainable, lr=args.learning_rate, alpha=0.5, k=6, N_sma_threshhold=5, betas=(.95, 0.999),
+                      eps=1e-5, weight_decay=args.weight_decay, use_gc=getattr(args, "use_gc", False),
+                      gc_conv_only=getattr(args, "gc_conv_only", False))

@@ -1,0 +1,118 @@
+"""Step bodies of the reference ``Engine`` (learning/engine.py) on the B200 path.
+
+Drop-in pieces (same names, argument meaning and return structure as the reference):
+  * ``compute_output(args, model, img, is_train)``   Engine._compute_output   (engine.py:298-310)
+  * ``compute_loss(args, criterion, outputs, label)`` Engine._compute_loss     (engine.py:312-333)
+  * ``apply_tta(args, model, img, tta_transforms)``   Engine._apply_tta        (engine.py:424-440)
+
+Fused fast path (what bench.py measures): ``predict_volume`` runs models x TTA variants x windows entirely on the
+GPU — windows are read out of the source volume through the variant's signed permutation, logits are blended
+with fp32 accumulators, de-augmented, sigmoid-ed and summed in place, and one final pass thresholds the mean and
+emits the BraTS label map with background removal (engine.py:236-252, utils/transforms.py:169-206,536-550).
+Nothing is copied to the host until the final uint8 labels.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .inferers import WindowPlan, accumulate_windows, sliding_window_inference
+from .tta import Compose, get_tta_transforms
+
+
+def _flatten(x):
+    if isinstance(x, (list, tuple)):
+        out = []
+        for y in x:
+            out.extend(_flatten(y))
+        return out
+    return [x]
+
+
+def _apply_f(seq, f):
+    if isinstance(seq, (list, tuple)):
+        return [_apply_f(s, f) for s in seq]
+    return f(seq)
+
+
+def compute_output(args, model, img, is_train: bool = False):
+    """autocast is a no-op here: the kernels already compute in bf16 with fp32 accumulation."""
+    if getattr(args, "sliding_window_inference", False) and not is_train:
+        return sliding_window_inference(img, roi_size=args.sliding_window_size, sw_batch_size=1, predictor=model,
+                                        device=torch.device("cpu"))
+    return model(img)
+
+
+def compute_loss(args, criterion, outputs, label=None):
+    if isinstance(outputs, (tuple, list)):  # deep supervision
+        heads = _flatten(outputs)
+        loss = torch.mean(torch.stack([criterion(h, label) for h in heads])) if label is not None else None
+        return heads[0], loss
+    return outputs, (criterion(outputs, label) if label is not None else None)
+
+
+def apply_tta(args, model, img, tta_transforms: Optional[Compose]) -> List:
+    """Drop-in Engine._apply_tta: list (one entry per variant) of de-augmented outputs moved to the CPU."""
+    outs = []
+    for tr in tta_transforms:
+        o = compute_output(args, model, tr.augment_image(img))
+        outs.append(_apply_f(o, lambda x: tr.deaugment_mask(x).cpu()))
+    return outs
+
+
+@torch.no_grad()
+def predict_volume(models: Sequence, image: torch.Tensor, tta_transforms: Optional[Compose] = None,
+                   sliding_window: bool = True, roi_size=(128, 128, 128), sw_batch_size: int = 4,
+                   overlap: float = 0.25, mode: str = "gaussian", sigma_scale: float = 0.125,
+                   logit_thresh: float = 0.5, remove_background: bool = True, return_prob: bool = False):
+    """Ensemble x TTA x sliding-window inference of ONE volume, fused on the GPU.
+
+    image: [1, C, D, H, W] fp32 on CUDA, spatial dims already divisible by 8 (shape_to_divisible).
+    Returns (onehot uint8 [1, 3, D, H, W] in (TC, WT, ET) order, label uint8 [1, 1, D, H, W]) and, optionally, the
+    mean probability map.  Equivalent reference flow: Engine.evaluate(use_tta=...) -> post_trans -> labels.
+    """
+    if image.dim() != 5 or image.shape[0] != 1:
+        raise ValueError("predict_volume takes one volume: [1, C, D, H, W]")
+    vol = image.detach().to(torch.float32).contiguous()
+    vdims = tuple(vol.shape[2:])
+    if tta_transforms is None:
+        variants = [((0, 1, 2), (0, 0, 0))]
+    else:
+        variants = []
+        for tr in tta_transforms:
+            if tr.variant is None:
+                raise ValueError("fused TTA needs signed-permutation transforms; use apply_tta for others")
+            variants.append(tr.variant)
+    k = models[0].num_classes
+    prob_sum = torch.zeros((k,) + vdims, dtype=torch.float32, device=vol.device)
+    acc_cache = {}
+    count = 0
+    for model in models:
+        model._ensure_packed()
+        for perm, flip in variants:
+            adims = [0, 0, 0]
+            for j in range(3):
+                adims[perm[j]] = vdims[j]
+            if sliding_window:
+                plan = WindowPlan(adims, roi_size, overlap, mode, sigma_scale, vol.device)
+                key = plan.image_size
+                if key not in acc_cache:
+                    acc_cache[key] = torch.empty((k,) + plan.image_size, dtype=torch.float32, device=vol.device)
+                acc = acc_cache[key]
+                acc.zero_()
+                accumulate_windows(vol, 0, model, plan, sw_batch_size, acc, (perm, flip))
+                ops.tta_accumulate(acc, plan.count, prob_sum, perm, flip, pad_before=plan.pad_before)
+            else:
+                # full-volume forward (the reference's default path, engine.py:309)
+                ws = model._ws.setdefault(("full",) + tuple(adims), {})
+                x8 = model._buf(ws, "x8", (1,) + tuple(adims) + (8,))
+                ops.pack_windows(vol, x8, [(0, 0, 0)], perm=perm, flip=flip)
+                logits, _ = model.forward_packed(x8, want_deep=False)
+                ops.tta_accumulate(logits[0], None, prob_sum, perm, flip)
+            count += 1
+    onehot, label = ops.labels_finalize(prob_sum, count, logit_thresh, image=vol[0] if remove_background else None)
+    if return_prob:
+        return onehot[None], label[None, None], prob_sum / count
+    return onehot[None], label[None, None]

@@ -1,0 +1,426 @@
+"""Drop-in EquiUnet (V1) and EquiUnetASSPEvo (V2) whose forward runs on the sm_100a kernels of libb21.so.
+
+Constructor signatures, ``forward`` return structure and ``state_dict`` keys/shapes are those of the reference
+(networks/equiunet2020.py:408-500, networks/equiunet2021.py:225-333), so reference
+checkpoints load unchanged.  torch.nn modules are used ONLY as parameter holders (same construction order as the
+reference, hence the same random init under the same seed); their forward is never called — there is no eager
+fallback, and a missing CUDA library raises.
+
+Internally activations are channels-last bf16 ([N, D, H, W, C]); channel concatenations are written in place as
+channel slices of one buffer; norm statistics come out of the conv epilogue.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+# ================================================================================================ holders
+def _conv3(cin, cout, dil=1, bias=False):
+    return nn.Conv3d(cin, cout, kernel_size=3, padding=dil, dilation=dil, bias=bias)
+
+
+def _conv1(cin, cout, bias=True):
+    return nn.Conv3d(cin, cout, kernel_size=1, bias=bias)
+
+
+class ConvBnRelu(nn.Sequential):
+    """Parameter holder mirroring equiunet2020.py:51-75 (conv -> GroupNorm(8) -> act -> dropout)."""
+
+    def __init__(self, cin, cout, act, dil=1, dropout=0.0):
+        super().__init__(OrderedDict([("conv", _conv3(cin, cout, dil)), ("bn", nn.GroupNorm(8, cout, affine=True)),
+                                      (act, nn.ReLU(inplace=True)), ("dropout", nn.Dropout(p=dropout))]))
+        self.dil = dil
+
+
+class UBlock(nn.Sequential):
+    def __init__(self, cin, mid, cout, act, dils=(1, 1), dropout=0.0):
+        super().__init__(OrderedDict([("ConvBnRelu1", ConvBnRelu(cin, mid, act, dils[0], dropout)),
+                                      ("ConvBnRelu2", ConvBnRelu(mid, cout, act, dils[1], dropout))]))
+
+
+class EvoNorm3D(nn.Module):
+    """Parameter holder for EvoNorm3D-S0 (equiunet2021.py:55-105): gamma, beta, (unused) v and running_var."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(1, c, 1, 1, 1))
+        self.beta = nn.Parameter(torch.zeros(1, c, 1, 1, 1))
+        self.v = nn.Parameter(torch.ones(1, c, 1, 1, 1))
+        self.register_buffer("running_var", torch.ones(1, c, 1, 1, 1))
+        self.eps = 1e-5
+
+
+class ResidualSELayer(nn.Module):
+    """Parameter holder for MONAI ResidualSELayer(r=2): keys fc.0.*, fc.2.*."""
+
+    def __init__(self, c, r=2):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(c, c // r), nn.ReLU(inplace=True), nn.Linear(c // r, c), nn.Sigmoid())
+
+
+class ConvEvoBlockCorrected(nn.Module):
+    def __init__(self, cin, cout, dropout):
+        super().__init__()
+        self.conv_conv_se = nn.Sequential(_conv3(cin, cout, bias=True), EvoNorm3D(cout), nn.Dropout(dropout),
+                                          _conv3(cout, cout, bias=True), EvoNorm3D(cout), nn.Dropout(dropout),
+                                          ResidualSELayer(cout))
+
+
+class ConvEvo(nn.Module):
+    def __init__(self, cin, cout, dropout):
+        super().__init__()
+        self.conv = _conv1(cin, cout)
+        self.evo = EvoNorm3D(cout)
+        self.drop = nn.Dropout(dropout)
+
+
+class SimpleASPPEVO(nn.Module):
+    def __init__(self, cin, cbranch, kernel_sizes=(1, 3, 3, 3), dilations=(1, 2, 4, 6)):
+        super().__init__()
+        if len(kernel_sizes) != len(dilations):
+            raise ValueError("kernel_sizes and dilations length must match, "
+                             f"got kernel_sizes={len(kernel_sizes)} dilations={len(dilations)}.")
+        self.dilations = tuple(dilations)
+        self.convs = nn.ModuleList()
+        for k, d in zip(kernel_sizes, dilations):
+            self.convs.append(nn.Conv3d(cin, cbranch, kernel_size=k, dilation=d, padding=(k - 1) // 2 * d))
+        self.conv_k1 = ConvEvo(cbranch * len(kernel_sizes), cbranch * len(kernel_sizes), 0)
+
+
+def _head(cin, ncls, scale):
+    return nn.Sequential(_conv1(cin, ncls), nn.Upsample(scale_factor=scale, mode="trilinear", align_corners=True))
+
+
+# ================================================================================================ runtime base
+class _B21Net(nn.Module):
+    """Shared runtime: weight packing cache, workspace cache, input packing."""
+
+    def _init_runtime(self):
+        self._packed: Dict[str, object] = {}
+        self._pack_key = None
+        self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self.skip_deep_heads_in_eval = False  # set by the inference wrappers (they discard the deep heads)
+
+    # ---- packing
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self):
+        key = self._param_key()
+        if key != self._pack_key:
+            self._packed = {}
+            self._pack()
+            self._pack_key = key
+
+    def _pc(self, name: str, conv: nn.Conv3d, cin_padded: Optional[int] = None):
+        self._packed[name] = ops.PackedConv(conv.weight, conv.bias, cin_padded=cin_padded)
+
+    def _vec(self, name: str, t: torch.Tensor):
+        self._packed[name] = t.detach().reshape(-1).to(torch.float32).contiguous()
+
+    def _mat(self, name: str, t: torch.Tensor):
+        self._packed[name] = t.detach().to(torch.float32).reshape(t.shape[0], -1).contiguous()
+
+    # ---- workspaces
+    def _buf(self, ws, name, shape, dtype=torch.bfloat16):
+        t = ws.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self._device())
+            ws[name] = t
+        return t
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("brats21_b200 networks run on CUDA only (no CPU fallback): move the input to a B200")
+        if x.dim() != 5 or x.shape[1] != self.inplanes:
+            raise ValueError(f"expected [N, {self.inplanes}, D, H, W], got {tuple(x.shape)}")
+        if any(s % 8 for s in x.shape[2:]):
+            raise ValueError(f"spatial dims must be divisible by 8 (shape_to_divisible), got {tuple(x.shape[2:])}")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())) \
+                and self.training:
+            from .autograd import network_forward_train  # noqa: WPS433 (lazy: training path)
+            return network_forward_train
+        return None
+
+    def pack_input(self, x: torch.Tensor) -> torch.Tensor:
+        """NCDHW fp32 -> channels-last bf16 with the 4 modalities padded to 8 channels."""
+        n, c, d, h, w = x.shape
+        x = x.detach().to(torch.float32).contiguous()
+        ws = self._ws.setdefault(("in", n, d, h, w), {})
+        out = self._buf(ws, "x8", (n, d, h, w, 8))
+        for b0 in range(0, n, 16):
+            nb = min(16, n - b0)
+            ops.pack_windows(x, out[b0:b0 + nb], [(0, 0, 0)] * nb, vol_index=list(range(b0, b0 + nb)))
+        return out
+
+    def forward(self, x: torch.Tensor):
+        train_fn = self._check_input(x)
+        if train_fn is not None:
+            return train_fn(self, x)
+        with torch.no_grad():
+            want_deep = self.deep_supervision and not (self.skip_deep_heads_in_eval and not self.training)
+            out, deeps = self.forward_packed(self.pack_input(x), want_deep)
+        if self.deep_supervision:
+            return out, deeps
+        return out
+
+
+# ================================================================================================ V1
+class EquiUnet(_B21Net):
+    """B200 EquiUnet (reference: networks/equiunet2020.py:408-500)."""
+    name = "EquiUnet"
+
+    def __init__(self, inplanes, num_classes, features, norm_layer=None, act="relu", deep_supervision=False,
+                 dropout=0, refinement=False):
+        super().__init__()
+        if norm_layer not in ("group",):
+            raise NotImplementedError("only norm_layer='group' (GroupNorm(8)) is on the accelerated path")
+        if act != "relu":
+            raise NotImplementedError("only act='relu' is on the accelerated V1 path")
+        if refinement:
+            raise NotImplementedError("refinement (RefUnet) is out of scope (SURVEY.md §0)")
+        if dropout:
+            raise NotImplementedError("dropout > 0 is not supported")
+        f = list(features)
+        self.inplanes, self.num_classes, self.features = inplanes, num_classes, f
+        self.deep_supervision, self.act, self.refinement = deep_supervision, act, refinement
+        self.encoder1 = UBlock(inplanes, f[0], f[0], act)
+        self.encoder2 = UBlock(f[0], f[1], f[1], act)
+        self.encoder3 = UBlock(f[1], f[2], f[2], act)
+        self.encoder4 = UBlock(f[2], f[3], f[3], act)
+        self.bottom = UBlock(f[3], f[3], f[3], act, (2, 2))
+        self.bottom_2 = ConvBnRelu(f[3] * 2, f[2], act)
+        self.downsample = nn.MaxPool3d(2, 2)
+        self.decoder3 = UBlock(f[2] * 2, f[2], f[1], act)
+        self.decoder2 = UBlock(f[1] * 2, f[1], f[0], act)
+        self.decoder1 = UBlock(f[0] * 2, f[0], f[0], act)
+        self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
+        self.outconv = _conv1(f[0], num_classes)
+        if deep_supervision:
+            self.deep_bottom = _head(f[3], num_classes, 8)
+            self.deep_bottom2 = _head(f[2], num_classes, 8)
+            self.deep3 = _head(f[1], num_classes, 4)
+            self.deep2 = _head(f[0], num_classes, 2)
+        # init_weights(self, "kaiming") (factory.py:203-224): kaiming-normal fan_out on every Conv weight
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight.data, a=0.0, mode="fan_out")
+        self._init_runtime()
+
+    _CBR = ["encoder1.ConvBnRelu1", "encoder1.ConvBnRelu2", "encoder2.ConvBnRelu1", "encoder2.ConvBnRelu2",
+            "encoder3.ConvBnRelu1", "encoder3.ConvBnRelu2", "encoder4.ConvBnRelu1", "encoder4.ConvBnRelu2",
+            "bottom.ConvBnRelu1", "bottom.ConvBnRelu2", "bottom_2", "decoder3.ConvBnRelu1", "decoder3.ConvBnRelu2",
+            "decoder2.ConvBnRelu1", "decoder2.ConvBnRelu2", "decoder1.ConvBnRelu1", "decoder1.ConvBnRelu2"]
+
+    def _pack(self):
+        for name in self._CBR:
+            m = self.get_submodule(name)
+            self._pc(name, m.conv, cin_padded=8 if name == "encoder1.ConvBnRelu1" else None)
+            self._vec(name + ".g", m.bn.weight)
+            self._vec(name + ".b", m.bn.bias)
+        heads = ["outconv"] + (["deep_bottom.0", "deep_bottom2.0", "deep3.0", "deep2.0"] if self.deep_supervision else [])
+        for name in heads:
+            m = self.get_submodule(name)
+            self._mat(name + ".w", m.weight)
+            self._vec(name + ".bias", m.bias)
+
+    def _cbr(self, name, x, out, stats, dil=1):
+        p = self._packed
+        ops.conv3d(x, p[name], out=out, stats=stats, dil=dil)
+        ops.norm_apply(out, stats, p[name + ".g"], p[name + ".b"], ops.GN_RELU)
+        return out
+
+    def forward_packed(self, x8: torch.Tensor, want_deep: bool = True):
+        """x8: [N, D, H, W, 8] bf16 channels-last (modalities in channels 0..3). Returns (logits, [deep heads])."""
+        self._ensure_packed()
+        n, d, h, w, _ = x8.shape
+        f = self.features
+        ws = self._ws.setdefault(("v1", n, d, h, w), {})
+        B = lambda name, s, c: self._buf(ws, name, (n, d // s, h // s, w // s, c))  # noqa: E731
+        stats = self._buf(ws, "stats", (ops._lib.STAT_SLOTS, n, 8, 2), torch.float64)
+        cat1, cat2, cat3, cat4 = B("cat1", 1, 2 * f[0]), B("cat2", 2, 2 * f[1]), B("cat3", 4, 2 * f[2]), B("cat4", 8, 2 * f[3])
+        t1, t2, t3, t4 = B("t1", 1, f[0]), B("t2", 2, f[1]), B("t3", 4, f[2]), B("t4", 8, f[3])
+        p1, p2, p3 = B("p1", 2, f[0]), B("p2", 4, f[1]), B("p3", 8, f[2])
+
+        self._cbr("encoder1.ConvBnRelu1", x8, t1, stats)
+        down1 = self._cbr("encoder1.ConvBnRelu2", t1, cat1[..., :f[0]], stats)
+        ops.scale_pool(down1, pooled=p1, mode=1)
+        self._cbr("encoder2.ConvBnRelu1", p1, t2, stats)
+        down2 = self._cbr("encoder2.ConvBnRelu2", t2, cat2[..., :f[1]], stats)
+        ops.scale_pool(down2, pooled=p2, mode=1)
+        self._cbr("encoder3.ConvBnRelu1", p2, t3, stats)
+        down3 = self._cbr("encoder3.ConvBnRelu2", t3, cat3[..., :f[2]], stats)
+        ops.scale_pool(down3, pooled=p3, mode=1)
+        self._cbr("encoder4.ConvBnRelu1", p3, t4, stats)
+        down4 = self._cbr("encoder4.ConvBnRelu2", t4, cat4[..., :f[3]], stats)
+        self._cbr("bottom.ConvBnRelu1", down4, t4, stats, dil=2)
+        bottom = self._cbr("bottom.ConvBnRelu2", t4, cat4[..., f[3]:], stats, dil=2)
+        b2 = self._cbr("bottom_2", cat4, B("b2", 8, f[2]), stats)
+        ops.upsample2x(b2, cat3[..., f[2]:])
+        self._cbr("decoder3.ConvBnRelu1", cat3, t3, stats)
+        u3 = self._cbr("decoder3.ConvBnRelu2", t3, B("u3", 4, f[1]), stats)
+        ops.upsample2x(u3, cat2[..., f[1]:])
+        self._cbr("decoder2.ConvBnRelu1", cat2, t2, stats)
+        u2 = self._cbr("decoder2.ConvBnRelu2", t2, B("u2", 2, f[0]), stats)
+        ops.upsample2x(u2, cat1[..., f[0]:])
+        self._cbr("decoder1.ConvBnRelu1", cat1, t1, stats)
+        u1 = self._cbr("decoder1.ConvBnRelu2", t1, B("u1", 1, f[0]), stats)
+        p = self._packed
+        out = ops.head_conv(u1, p["outconv.w"], p["outconv.bias"])
+        deeps: List[torch.Tensor] = []
+        if want_deep and self.deep_supervision:
+            for name, src, s in (("deep_bottom.0", bottom, 8), ("deep_bottom2.0", b2, 8), ("deep3.0", u3, 4),
+                                 ("deep2.0", u2, 2)):
+                deeps.append(ops.upsample_f32(ops.head_conv(src, p[name + ".w"], p[name + ".bias"]), s))
+        return out, deeps
+
+
+# ================================================================================================ V2
+class EquiUnetASSPEvo(_B21Net):
+    """B200 EquiUnet-ASPP-Evo (reference: networks/equiunet2021.py:225-333)."""
+    name = "EquiUnetASSPEvo"
+
+    def __init__(self, inplanes, num_classes, features, norm_layer=None, act="relu", deep_supervision=False,
+                 dropout=0, refinement=False):
+        super().__init__()
+        warnings.warn("norm layer and activation specified will not be used ! only EVO !!")  # as the reference
+        if refinement:
+            raise NotImplementedError("refinement is broken in the reference (equiunet2021.py:237,282) — out of scope")
+        if dropout:
+            raise NotImplementedError("dropout > 0 is not supported")
+        f = list(features)
+        if f[0] % 16:
+            raise ValueError("EvoNorm groups=8 on width/2 channels needs width to be a multiple of 16")
+        self.inplanes, self.num_classes, self.features = inplanes, num_classes, f
+        self.deep_supervision, self.act, self.refinement = deep_supervision, act.upper(), refinement
+        self.encoder1 = ConvEvoBlockCorrected(inplanes, f[0], dropout)
+        self.encoder2 = ConvEvoBlockCorrected(2 * f[0], f[1], dropout)
+        self.encoder3 = ConvEvoBlockCorrected(2 * f[1], f[2], dropout)
+        self.encoder4 = ConvEvoBlockCorrected(2 * f[2], f[3], dropout)
+        self.bridge1 = ConvEvo(f[0], f[0] // 2, dropout)
+        self.bridge2 = ConvEvo(f[1], f[1] // 2, dropout)
+        self.bridge3 = ConvEvo(f[2], f[2] // 2, dropout)
+        self.aspp = SimpleASPPEVO(f[3], f[3] // 4)
+        self.downsample = nn.Identity()  # MONAI MaxAvgPool has no parameters; fused into scale_pool
+        self.upconv3 = ConvEvo(f[3], f[3] // 4, dropout)
+        self.decoder3 = ConvEvoBlockCorrected(f[2], f[2], dropout)
+        self.upconv2 = ConvEvo(f[2], f[2] // 4, dropout)
+        self.decoder2 = ConvEvoBlockCorrected(f[1], f[1], dropout)
+        self.upconv1 = ConvEvo(f[1], f[1] // 4, dropout)
+        self.decoder1 = ConvEvoBlockCorrected(f[0], f[0], dropout)
+        self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
+        self.out_conv = _conv1(f[0], num_classes)
+        if deep_supervision:
+            self.deep3 = _head(f[2], num_classes, 4)
+            self.deep2 = _head(f[1], num_classes, 2)
+        self._init_runtime()
+
+    _BLOCKS = ["encoder1", "encoder2", "encoder3", "encoder4", "decoder3", "decoder2", "decoder1"]
+    _CONVEVO = ["bridge1", "bridge2", "bridge3", "aspp.conv_k1", "upconv3", "upconv2", "upconv1"]
+
+    def _pack(self):
+        for b in self._BLOCKS:
+            seq = self.get_submodule(b).conv_conv_se
+            self._pc(b + ".c0", seq[0], cin_padded=8 if b == "encoder1" else None)
+            self._pc(b + ".c1", seq[3])
+            for tag, evo in (("e0", seq[1]), ("e1", seq[4])):
+                self._vec(f"{b}.{tag}.g", evo.gamma)
+                self._vec(f"{b}.{tag}.b", evo.beta)
+            fc = seq[6].fc
+            self._mat(b + ".se.w1", fc[0].weight)
+            self._vec(b + ".se.b1", fc[0].bias)
+            self._mat(b + ".se.w2", fc[2].weight)
+            self._vec(b + ".se.b2", fc[2].bias)
+        for name in self._CONVEVO:
+            m = self.get_submodule(name)
+            self._pc(name, m.conv)
+            self._vec(name + ".g", m.evo.gamma)
+            self._vec(name + ".b", m.evo.beta)
+        for i, conv in enumerate(self.aspp.convs):
+            self._pc(f"aspp.convs.{i}", conv)
+        heads = ["out_conv"] + (["deep3.0", "deep2.0"] if self.deep_supervision else [])
+        for name in heads:
+            m = self.get_submodule(name)
+            self._mat(name + ".w", m.weight)
+            self._vec(name + ".bias", m.bias)
+
+    def _block(self, name, x, tmp, out, stats, csum):
+        """conv-evo-conv-evo + SE gate; returns (pre-scale activations in `out`, scale [N, C])."""
+        p = self._packed
+        ops.conv3d(x, p[name + ".c0"], out=tmp, stats=stats)
+        ops.norm_apply(tmp, stats, p[name + ".e0.g"], p[name + ".e0.b"], ops.EVO_S0)
+        ops.conv3d(tmp, p[name + ".c1"], out=out, stats=stats)
+        csum.zero_()
+        ops.norm_apply(out, stats, p[name + ".e1.g"], p[name + ".e1.b"], ops.EVO_S0, chan_sum=csum)
+        n, d, h, w, _ = out.shape
+        scale = ops.se_gate(csum, p[name + ".se.w1"], p[name + ".se.b1"], p[name + ".se.w2"], p[name + ".se.b2"],
+                            d * h * w)
+        return out, scale
+
+    def _convevo(self, name, x, out, stats):
+        p = self._packed
+        ops.conv3d(x, p[name], out=out, stats=stats)
+        ops.norm_apply(out, stats, p[name + ".g"], p[name + ".b"], ops.EVO_S0)
+        return out
+
+    def forward_packed(self, x8: torch.Tensor, want_deep: bool = True):
+        self._ensure_packed()
+        n, d, h, w, _ = x8.shape
+        f = self.features
+        ws = self._ws.setdefault(("v2", n, d, h, w), {})
+        B = lambda name, s, c: self._buf(ws, name, (n, d // s, h // s, w // s, c))  # noqa: E731
+        stats = self._buf(ws, "stats", (ops._lib.STAT_SLOTS, n, 8, 2), torch.float64)
+        cs = [self._buf(ws, f"csum{i}", (n, f[i]), torch.float32) for i in range(4)]
+        t1, t2, t3, t4 = B("t1", 1, f[0]), B("t2", 2, f[1]), B("t3", 4, f[2]), B("t4", 8, f[3])
+        d1, d2, d3, d4 = B("d1", 1, f[0]), B("d2", 2, f[1]), B("d3", 4, f[2]), B("d4", 8, f[3])
+        p1, p2, p3 = B("p1", 2, 2 * f[0]), B("p2", 4, 2 * f[1]), B("p3", 8, 2 * f[2])
+        cat1, cat2, cat3 = B("cat1", 1, f[0]), B("cat2", 2, f[1]), B("cat3", 4, f[2])
+
+        _, s = self._block("encoder1", x8, t1, d1, stats, cs[0])
+        ops.scale_pool(d1, s, full=d1, pooled=p1, mode=2)
+        _, s = self._block("encoder2", p1, t2, d2, stats, cs[1])
+        ops.scale_pool(d2, s, full=d2, pooled=p2, mode=2)
+        _, s = self._block("encoder3", p2, t3, d3, stats, cs[2])
+        ops.scale_pool(d3, s, full=d3, pooled=p3, mode=2)
+        _, s = self._block("encoder4", p3, t4, d4, stats, cs[3])
+        ops.scale_pool(d4, s, full=d4, mode=0)
+
+        pk = self._packed
+        acat = B("asppcat", 8, f[3])
+        q = f[3] // 4
+        for i, dil in enumerate(self.aspp.dilations):
+            ops.conv3d(d4, pk[f"aspp.convs.{i}"], out=acat[..., i * q:(i + 1) * q], dil=dil)
+        assp = self._convevo("aspp.conv_k1", acat, t4, stats)
+
+        self._convevo("bridge1", d1, cat1[..., :f[0] // 2], stats)
+        self._convevo("bridge2", d2, cat2[..., :f[1] // 2], stats)
+        self._convevo("bridge3", d3, cat3[..., :f[2] // 2], stats)
+
+        u = self._convevo("upconv3", assp, B("uc3", 8, f[3] // 4), stats)
+        ops.upsample2x(u, cat3[..., f[2] // 2:])
+        up3, s = self._block("decoder3", cat3, t3, B("up3", 4, f[2]), stats, cs[2])
+        ops.scale_pool(up3, s, full=up3, mode=0)
+        u = self._convevo("upconv2", up3, B("uc2", 4, f[2] // 4), stats)
+        ops.upsample2x(u, cat2[..., f[1] // 2:])
+        up2, s = self._block("decoder2", cat2, t2, B("up2", 2, f[1]), stats, cs[1])
+        ops.scale_pool(up2, s, full=up2, mode=0)
+        u = self._convevo("upconv1", up2, B("uc1", 2, f[1] // 4), stats)
+        ops.upsample2x(u, cat1[..., f[0] // 2:])
+        up1, s1 = self._block("decoder1", cat1, t1, B("up1", 1, f[0]), stats, cs[0])
+        # the SE scale of decoder1 is folded into the 1x1 head: W (x * s) == (W * s) x
+        out = ops.head_conv(up1, pk["out_conv.w"], pk["out_conv.bias"], scale=s1)
+        deeps: List[torch.Tensor] = []
+        if want_deep and self.deep_supervision:
+            deeps.append(ops.upsample_f32(ops.head_conv(up3, pk["deep3.0.w"], pk["deep3.0.bias"]), 4))
+            deeps.append(ops.upsample_f32(ops.head_conv(up2, pk["deep2.0.w"], pk["deep2.0.bias"]), 2))
+        return out, deeps

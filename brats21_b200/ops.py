@@ -53,3 +53,116 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
     call("b21_conv3d_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
          n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- norm / SE / pool
+GN_RELU, EVO_S0 = 0, 1
+
+
+def norm_apply(x, stats, gamma, beta, mode, out=None, chan_sum=None, eps=1e-5):
+    """GroupNorm(8)+ReLU or EvoNorm-S0 from conv-epilogue statistics; in place when out is None."""
+    n, d, h, w, c = x.shape
+    if out is None:
+        out = x
+    call("b21_norm_apply", ptr(x), _ld(x), ptr(out), _ld(out), ptr(stats), ptr(gamma), ptr(beta), ptr(chan_sum),
+         mode, n, d * h * w, c, eps, stream_ptr())
+    return out
+
+
+def se_gate(chan_sum, w1, b1, w2, b2, nvox):
+    n, c = chan_sum.shape
+    scale = torch.empty_like(chan_sum)
+    call("b21_se_gate", ptr(chan_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(scale), n, c, w1.shape[0],
+         1.0 / float(nvox), stream_ptr())
+    return scale
+
+
+def scale_pool(x, scale=None, full=None, pooled=None, mode=0):
+    """mode 0: full = x*scale; 1: max-pool; 2: [max|avg]-pool (writes 2C channels)."""
+    n, d, h, w, c = x.shape
+    call("b21_scale_pool", ptr(x), _ld(x), ptr(scale), ptr(full), _ld(full) if full is not None else 0,
+         ptr(pooled), _ld(pooled) if pooled is not None else 0, mode, n, d, h, w, c, stream_ptr())
+
+
+def upsample2x(x, out):
+    n, d, h, w, c = x.shape
+    assert out.shape == (n, 2 * d, 2 * h, 2 * w, c)
+    call("b21_upsample2x", ptr(x), _ld(x), ptr(out), _ld(out), n, d, h, w, c, stream_ptr())
+    return out
+
+
+def upsample_f32(x, s):
+    """[N, K, d, h, w] fp32 -> [N, K, s*d, s*h, s*w] (trilinear, align_corners=True)."""
+    n, k, d, h, w = x.shape
+    out = torch.empty((n, k, s * d, s * h, s * w), dtype=torch.float32, device=x.device)
+    call("b21_upsample_f32", ptr(x.contiguous()), ptr(out), n * k, d, h, w, s, stream_ptr())
+    return out
+
+
+def head_conv(x, weight, bias, scale=None, out=None):
+    """1x1 conv to <=4 classes; returns NCDHW fp32 logits.  weight fp32 [K, C]."""
+    n, d, h, w, c = x.shape
+    k = weight.shape[0]
+    if out is None:
+        out = torch.empty((n, k, d, h, w), dtype=torch.float32, device=x.device)
+    call("b21_head_conv", ptr(x), _ld(x), ptr(scale), ptr(weight), ptr(bias), ptr(out), n, d * h * w, c, k,
+         stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- inference wrappers
+import ctypes as _C
+
+
+def _iarr(vals):
+    vals = [int(v) for v in vals]
+    return (_C.c_int * len(vals))(*vals)
+
+
+def pack_windows(vol, out, origins, perm=(0, 1, 2), flip=(0, 0, 0), vol_index=None):
+    """vol [Nv, C, D, H, W] fp32 -> out [B, d, h, w, cpad] bf16 windows of the augmented volume."""
+    nv, vc, vd, vh, vw = vol.shape
+    b, d, h, w, cpad = out.shape
+    assert vol.dtype == torch.float32 and vol.is_contiguous() and out.is_contiguous() and len(origins) == b
+    flat = [c for o in origins for c in o]
+    call("b21_pack_windows", ptr(vol), vc, vd, vh, vw, ptr(out), cpad, b, d, h, w, _iarr(flat),
+         _iarr(vol_index) if vol_index is not None else None, _iarr(perm), _iarr(flip), stream_ptr())
+    return out
+
+
+def blend_accumulate(logits, acc, profiles, origins):
+    """acc [K, AD, AH, AW] += outer(profiles) * logits [B, K, d, h, w]; logits None -> count map (K = 1)."""
+    k, ad, ah, aw = acc.shape
+    pd, ph, pw = profiles
+    d, h, w = pd.numel(), ph.numel(), pw.numel()
+    nwin = len(origins)
+    if logits is not None:
+        assert logits.shape == (nwin, k, d, h, w) and logits.is_contiguous() and logits.dtype == torch.float32
+    flat = [c for o in origins for c in o]
+    call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
+         _iarr(flat), stream_ptr())
+
+
+def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_before=None, apply_sigmoid=True,
+                   overwrite=False):
+    k, ad, ah, aw = acc.shape
+    k2, vd, vh, vw = prob_sum.shape
+    assert k == k2 and acc.is_contiguous() and prob_sum.is_contiguous()
+    call("b21_tta_accumulate", ptr(acc), ptr(cnt), ptr(prob_sum), k, ad, ah, aw,
+         _iarr(pad_before) if pad_before is not None else None, vd, vh, vw, _iarr(perm), _iarr(flip),
+         int(apply_sigmoid), int(overwrite), stream_ptr())
+
+
+def labels_finalize(prob_sum, count, thresh=0.5, image=None, want_onehot=True, want_label=True, et_label=4):
+    k, vd, vh, vw = prob_sum.shape
+    assert k == 3
+    nvox = vd * vh * vw
+    onehot = torch.empty((3, vd, vh, vw), dtype=torch.uint8, device=prob_sum.device) if want_onehot else None
+    label = torch.empty((vd, vh, vw), dtype=torch.uint8, device=prob_sum.device) if want_label else None
+    ic = 0
+    if image is not None:
+        assert image.dtype == torch.float32 and image.is_contiguous() and image.shape[-3:] == (vd, vh, vw)
+        ic = image.shape[-4]
+    call("b21_labels_finalize", ptr(prob_sum), float(count), float(thresh), ptr(image), ic, ptr(onehot), ptr(label),
+         nvox, et_label, stream_ptr())
+    return onehot, label

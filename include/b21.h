@@ -57,6 +57,68 @@ int b21_conv3d_fwd(const void* x, int ldx, const void* w_packed, const float* bi
                    double* stats, int n, int d, int h, int w, int cin, int cout, int taps, int dil,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------- normalisation / SE
+ * norm_apply: y = GroupNorm(8,C)(x) -> ReLU (mode 0; networks/factory.py:182 + equiunet2020.py:60-61) or
+ * EvoNorm3D-S0 (mode 1; networks/equiunet2021.py:48-52,95-105: x*sigmoid(x)/sqrt(var_unbiased+eps)*gamma+beta)
+ * from the statistics buffer b21_conv3d_fwd filled.  x may alias y.  If chan_sum != NULL (fp32 [n][c], zeroed by
+ * the caller) the per-channel sums of the outputs are accumulated into it (squeeze-excite mean). */
+int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const double* stats, const float* gamma,
+                   const float* beta, float* chan_sum, int mode, int n, long long nvox, int c, float eps,
+                   void* stream);
+
+/* MONAI ResidualSELayer(r=2, relu, sigmoid) gate used at networks/equiunet2021.py:204-205:
+ * scale[n][c] = 1 + sigmoid(W2 relu(W1 (chan_sum[n] * inv_count) + b1) + b2), so that x + x*s == x*scale. */
+int b21_se_gate(const float* chan_sum, const float* w1, const float* b1, const float* w2, const float* b2,
+                float* scale, int n, int c, int hidden, float inv_count, void* stream);
+
+/* x*scale[n][c] written full-res (`full`, may alias x, may be NULL) and/or pooled 2x2x2 (`pooled`):
+ * mode 0 = scale only, 1 = nn.MaxPool3d(2,2) (equiunet2020.py:433), 2 = MONAI MaxAvgPool -> [max | avg] channel
+ * concat, 2c channels (equiunet2021.py:261).  scale may be NULL (= 1). */
+int b21_scale_pool(const void* x, int ldx, const float* scale, void* full, int ldfull, void* pooled, int ldpool,
+                   int mode, int n, int d, int h, int w, int c, void* stream);
+
+/* nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True) (equiunet2020.py:439, equiunet2021.py:270),
+ * ndhwc bf16 [n,d,h,w,c] -> [n,2d,2h,2w,c] written into a channel slice (ldy). */
+int b21_upsample2x(const void* x, int ldx, void* y, int ldy, int n, int d, int h, int w, int c, void* stream);
+
+/* Same interpolation by an integer factor s on ncdhw fp32 planes (deep-supervision heads,
+ * equiunet2020.py:444-458, equiunet2021.py:274-280). */
+int b21_upsample_f32(const float* x, float* y, int planes, int d, int h, int w, int s, void* stream);
+
+/* conv1x1 to k<=4 classes (outconv / out_conv / deep heads: equiunet2020.py:441-458, equiunet2021.py:271-280):
+ * out (ncdhw fp32 [n][k][nvox]) = b + W (x * scale[n]) ; scale may be NULL. */
+int b21_head_conv(const void* x, int ldx, const float* scale, const float* w, const float* b, float* out, int n,
+                  long long nvox, int c, int k, void* stream);
+
+/* ------------------------------------------------------------------------- sliding window / TTA / labels
+ * A TTA variant is (perm[3], flip[3]): augmented[a0,a1,a2] = volume[s0,s1,s2] with
+ * s_j = flip[j] ? dim_j-1-a_{perm[j]} : a_{perm[j]}  (tta/transforms.py:16-98,149-173 are all of this form).
+ *
+ * pack_windows: crop `nwin` (<=16) windows of size d,h,w at `origins` ([nwin][3], augmented frame, may be
+ * negative = zero padding as F.pad in utils/inferers.py:101-109) out of ncdhw fp32 volumes and write ndhwc bf16
+ * [nwin][d][h][w][cpad] (channels >= vc are zero).  Replaces augment_image + the slice/cat at inferers.py:126-132. */
+int b21_pack_windows(const float* vol, int vc, int vd, int vh, int vw, void* out, int cpad, int nwin, int d, int h,
+                     int w, const int* origins, const int* vol_index, const int* perm, const int* flip, void* stream);
+
+/* acc[k][ad][ah][aw] (+)= prof_d[z]*prof_h[y]*prof_w[x] * logits[win][k][z][y][x] for each window
+ * (utils/inferers.py:149-151; importance map = outer product of the three 1-D profiles).  logits == NULL
+ * accumulates the weights themselves (the count map, k = 1). */
+int b21_blend_accumulate(const float* logits, float* acc, const float* prof_d, const float* prof_h,
+                         const float* prof_w, int nwin, int k, int d, int h, int w, int ad, int ah, int aw,
+                         const int* origins, void* stream);
+
+/* prob_sum[k][vd][vh][vw] (+)= sigmoid(acc/cnt) de-augmented (inferers.py:154-162 + deaugment_mask +
+ * engine.py:239-249).  cnt may be NULL; pad_before = the F.pad offsets of the augmented frame (or NULL). */
+int b21_tta_accumulate(const float* acc, const float* cnt, float* prob_sum, int k, int ad, int ah, int aw,
+                       const int* pad_before, int vd, int vh, int vw, const int* perm, const int* flip,
+                       int apply_sigmoid, int overwrite, void* stream);
+
+/* (prob_sum / count >= thresh) -> onehot uint8 [3][nvox] (TC, WT, ET), zeroed where every image channel is 0
+ * (remove_background_voxels, utils/transforms.py:536-550), and the BraTS label map uint8 [nvox]
+ * (ConvertToBratsClassesBasedOnMultiChannel + ChangeLabel3To4, utils/transforms.py:169-206). */
+int b21_labels_finalize(const float* prob_sum, float count, float thresh, const float* image, int image_channels,
+                        uint8_t* onehot, uint8_t* label, long long nvox, int et_label, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
