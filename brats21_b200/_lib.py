@@ -81,6 +81,13 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name: str, *args):
+# kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
+_LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv3d_fwd": 1}
+launch_count = 0
+
+
+def call(name: str, *args, launches: int = None):
+    global launch_count
     lib = load()
     check(getattr(lib, name)(*args), name)
+    launch_count += _LAUNCHES.get(name, 1) if launches is None else launches

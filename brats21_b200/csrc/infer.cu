@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(256) blend_accumulate_kernel(const float* __re
     const int y = int(v % h); v /= h;
     const int z = int(v % d);
     const int k = int(v / d);
-    const float wt = __ldg(pd + z) * __ldg(ph + y) * __ldg(pw + x);
+    const float wt = __fmul_rn(__fmul_rn(__ldg(pd + z), __ldg(ph + y)), __ldg(pw + x));
     const size_t ai = ((size_t(k) * AD + (o0 + z)) * AH + (o1 + y)) * AW + (o2 + x);
-    acc[ai] += wt * (logits ? __ldg(logits + i) : 1.f);
+    // separate multiply and add (no FMA contraction): the reference does `out += importance_map * seg_prob`
+    acc[ai] = __fadd_rn(acc[ai], logits ? __fmul_rn(wt, __ldg(logits + i)) : wt);
   }
 }
 

@@ -29,7 +29,7 @@ class PackedConv:
         if cin_padded is None:
             cin_padded = (inner + 7) // 8 * 8
         self.k, self.taps = k, k ** 3
-        self.cout, self.cin = rows, cin_padded
+        self.cout, self.cin, self.cin_true = rows, cin_padded, inner
         self.cout_padded = _lib.load().b21_conv_cout_padded(rows)
         self.w = torch.empty((self.taps, self.cout_padded, cin_padded), dtype=torch.bfloat16, device=weight.device)
         w32 = weight.detach().to(torch.float32).contiguous()
@@ -50,9 +50,22 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
     if out is None:
         out = torch.empty((n, d, h, w, pw.cout), dtype=torch.bfloat16, device=x.device)
     assert out.shape == (n, d, h, w, pw.cout) and out.dtype == torch.bfloat16
+    prof = conv_profile
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("b21_conv3d_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
          n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (cin, pw.cout, pw.taps, d)))
     return out
+
+
+# When set to a list, every conv launch appends (start_event, end_event, algorithmic_flops, shape_key):
+# bench.py uses it to time the dominant kernel live with CUDA events on the launching stream.
+conv_profile = None
 
 
 # ---------------------------------------------------------------------------------------------- norm / SE / pool
@@ -140,7 +153,7 @@ def blend_accumulate(logits, acc, profiles, origins):
         assert logits.shape == (nwin, k, d, h, w) and logits.is_contiguous() and logits.dtype == torch.float32
     flat = [c for o in origins for c in o]
     call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
-         _iarr(flat), stream_ptr())
+         _iarr(flat), stream_ptr(), launches=nwin)
 
 
 def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_before=None, apply_sigmoid=True,

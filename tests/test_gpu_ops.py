@@ -1,0 +1,172 @@
+"""GPU parity of each kernel family (through the C-ABI) against the oracle / plain torch fp32 on identical inputs.
+Tolerances: bf16 storage => 2^-8 relative per rounding; integer/byte outputs are bit-exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _cl(x):  # NCDHW -> channels-last bf16
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+
+
+def _nc(x):  # channels-last -> NCDHW fp32
+    return x.float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,shape", [
+    (48, 48, 3, 1, (1, 16, 16, 16)), (8, 48, 3, 1, (2, 8, 16, 8)), (96, 96, 3, 1, (1, 8, 8, 16)),
+    (384, 384, 3, 2, (1, 8, 8, 8)), (384, 96, 3, 6, (1, 16, 16, 16)), (768, 192, 3, 1, (1, 4, 8, 8)),
+    (48, 24, 1, 1, (1, 16, 8, 8)), (16, 16, 3, 1, (1, 5, 7, 9)), (64, 64, 3, 4, (1, 2, 2, 2))])
+def test_conv3d_matches_torch(cin, cout, k, dil, shape):
+    from brats21_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin * 1000 + cout + dil)
+    n, d, h, w = shape
+    x = torch.randn((n, cin, d, h, w), device=DEV, generator=g)
+    wt = torch.randn((cout, cin, k, k, k), device=DEV, generator=g) / (cin * k ** 3) ** 0.5
+    b = torch.randn((cout,), device=DEV, generator=g)
+    xb = _cl(x)
+    st = ops.new_stats(n, DEV)
+    y = ops.conv3d(xb, ops.PackedConv(wt, b), stats=st, dil=dil)
+    ref = F.conv3d(xb.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), b,
+                   padding=dil if k == 3 else 0, dilation=dil)
+    assert (_nc(y) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()  # one bf16 rounding of the output
+    r = ref.reshape(n, 8, cout // 8, -1).double()
+    s = st.sum(0)
+    assert torch.allclose(s[..., 0], r.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+
+
+def test_conv3d_argument_errors():
+    from brats21_b200 import ops
+    x = torch.zeros((1, 4, 4, 4, 12), device=DEV, dtype=torch.bfloat16)
+    pw = ops.PackedConv(torch.zeros((8, 16, 1, 1, 1), device=DEV), None)
+    with pytest.raises((RuntimeError, AssertionError)):
+        ops.conv3d(x, pw)
+
+
+@pytest.mark.parametrize("mode", ["gn", "evo"])
+@pytest.mark.parametrize("c,shape", [(48, (2, 8, 8, 8)), (16, (1, 4, 6, 10)), (384, (1, 4, 4, 4))])
+def test_norm_apply_matches_oracle(mode, c, shape):
+    from brats21_b200 import ops
+    from oracle import nets
+    g = torch.Generator(device=DEV).manual_seed(c)
+    n, d, h, w = shape
+    x = torch.randn((n, c, d, h, w), device=DEV, generator=g) * 1.7 + 0.3
+    gamma = 1 + 0.2 * torch.randn(c, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(c, device=DEV, generator=g)
+    xb = _cl(x)
+    xq = _nc(xb)
+    # statistics exactly as the conv epilogue would deliver them (fp64 sums of the fp32 values)
+    st = torch.zeros((32, n, 8, 2), dtype=torch.float64, device=DEV)
+    r = xq.reshape(n, 8, -1).double()
+    st[3, :, :, 0] = r.sum(-1)
+    st[7, :, :, 1] = (r * r).sum(-1)
+    csum = torch.zeros((n, c), device=DEV)
+    out = torch.empty_like(xb)
+    ops.norm_apply(xb, st, gamma, beta, ops.GN_RELU if mode == "gn" else ops.EVO_S0, out=out, chan_sum=csum)
+    ref = nets.group_norm_relu(xq, gamma, beta) if mode == "gn" else nets.evonorm_s0(xq, gamma, beta)
+    assert (_nc(out) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
+    assert torch.allclose(csum, _nc(out).sum(dim=(2, 3, 4)), rtol=1e-3, atol=1e-2)
+    # in place
+    ops.norm_apply(xb, st, gamma, beta, ops.GN_RELU if mode == "gn" else ops.EVO_S0)
+    assert torch.equal(xb, out)
+
+
+def test_se_gate_scale_pool_upsample_head():
+    from brats21_b200 import ops
+    from oracle import nets
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n, c, d, h, w = 2, 32, 8, 12, 16
+    x = torch.randn((n, c, d, h, w), device=DEV, generator=g)
+    xb = _cl(x)
+    xq = _nc(xb)
+    w1, b1 = torch.randn((c // 2, c), device=DEV, generator=g) * 0.3, torch.randn(c // 2, device=DEV, generator=g) * 0.1
+    w2, b2 = torch.randn((c, c // 2), device=DEV, generator=g) * 0.3, torch.randn(c, device=DEV, generator=g) * 0.1
+    csum = xq.sum(dim=(2, 3, 4))
+    scale = ops.se_gate(csum, w1, b1, w2, b2, d * h * w)
+    ref_scale = 1 + torch.sigmoid(F.linear(torch.relu(F.linear(xq.mean(dim=(2, 3, 4)), w1, b1)), w2, b2))
+    assert torch.allclose(scale, ref_scale, rtol=1e-5, atol=1e-5)
+    se_ref = nets.residual_se(xq, w1, b1, w2, b2)
+    full = torch.empty_like(xb)
+    pooled = torch.zeros((n, d // 2, h // 2, w // 2, 2 * c + 8), device=DEV, dtype=torch.bfloat16)
+    ops.scale_pool(xb, scale, full=full, pooled=pooled[..., :2 * c], mode=2)
+    assert (_nc(full) - se_ref).abs().max().item() <= 2 ** -7 * se_ref.abs().max().item()
+    ref_pool = nets.max_avg_pool(_nc(full))
+    assert (_nc(pooled[..., :2 * c]) - ref_pool).abs().max().item() <= 2 ** -7 * ref_pool.abs().max().item()
+    assert (pooled[..., 2 * c:] == 0).all()
+    mp = torch.empty((n, d // 2, h // 2, w // 2, c), device=DEV, dtype=torch.bfloat16)
+    ops.scale_pool(xb, None, pooled=mp, mode=1)
+    assert torch.equal(_nc(mp), F.max_pool3d(xq, 2))
+    up = torch.zeros((n, 2 * d, 2 * h, 2 * w, 2 * c), device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x(xb, up[..., c:])
+    ref_up = nets.up_trilinear(xq, 2)
+    assert (_nc(up[..., c:]) - ref_up).abs().max().item() <= 2 ** -7 * ref_up.abs().max().item()
+    hw, hb = torch.randn((3, c), device=DEV, generator=g) * 0.2, torch.randn(3, device=DEV, generator=g)
+    logits = ops.head_conv(xb, hw, hb, scale=scale)
+    ref_logits = F.conv3d(xq * scale.reshape(n, c, 1, 1, 1), hw.reshape(3, c, 1, 1, 1), hb)
+    assert torch.allclose(logits, ref_logits, rtol=1e-4, atol=1e-4)
+    for s in (2, 4, 8):
+        small = logits[:, :, :4, :6, :8].contiguous()
+        assert torch.allclose(ops.upsample_f32(small, s), nets.up_trilinear(small, s), rtol=1e-5, atol=1e-5)
+
+
+def test_pack_blend_tta_labels_bit_exact():
+    from brats21_b200 import ops, tta
+    from oracle import inference as oinf
+    g = torch.Generator(device=DEV).manual_seed(9)
+    vol = torch.randn((2, 4, 12, 10, 14), device=DEV, generator=g)
+    for tr in list(tta.get_tta_transforms()) + list(tta.get_flip8_transforms()):
+        perm, flip = tr.variant
+        aug = tr.augment_image(vol).contiguous()
+        ad = aug.shape[2:]
+        out = torch.empty((2, 8, 8, 8, 8), device=DEV, dtype=torch.bfloat16)
+        origins = [(1, 0, 2), (-3, 2, ad[2] - 6)]  # second window hangs over both ends -> zero padding
+        ops.pack_windows(vol, out, origins, perm=perm, flip=flip, vol_index=[0, 1])
+        for b, o in enumerate(origins):
+            ref = torch.zeros((4, 8, 8, 8), device=DEV)
+            lo = [max(0, -c) for c in o]
+            hi = [min(8, ad[j] - o[j]) for j in range(3)]
+            ref[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = aug[b, :, o[0] + lo[0]:o[0] + hi[0], o[1] + lo[1]:o[1] + hi[1],
+                                                                o[2] + lo[2]:o[2] + hi[2]]
+            got = out[b].float().permute(3, 0, 1, 2)
+            assert torch.equal(got[:4], ref.to(torch.bfloat16).float())
+            assert (got[4:] == 0).all()
+        # de-augmentation: prob_sum += sigmoid(acc / cnt) scattered back
+        acc = torch.randn((3,) + tuple(ad), device=DEV, generator=g)
+        cnt = torch.rand((1,) + tuple(ad), device=DEV, generator=g) + 0.5
+        ps = torch.full((3, 12, 10, 14), 0.25, device=DEV)
+        ops.tta_accumulate(acc, cnt, ps, perm, flip)
+        ref = 0.25 + tr.deaugment_mask(torch.sigmoid(acc / cnt)[None])[0]
+        assert torch.allclose(ps, ref, rtol=1e-6, atol=1e-6)
+    # blending: fp32, same operation order as the reference loop => bit-exact against torch on the GPU
+    prof = [torch.rand(8, device=DEV, generator=g) + 0.1 for _ in range(3)]
+    logits = torch.randn((3, 3, 8, 8, 8), device=DEV, generator=g)
+    acc = torch.zeros((3, 12, 10, 14), device=DEV)
+    origins = [(0, 0, 0), (4, 2, 6), (2, 1, 3)]
+    ops.blend_accumulate(logits, acc, prof, origins)
+    ref = torch.zeros_like(acc)
+    wmap = prof[0].reshape(-1, 1, 1) * prof[1].reshape(1, -1, 1) * prof[2].reshape(1, 1, -1)
+    for j, o in enumerate(origins):
+        ref[:, o[0]:o[0] + 8, o[1]:o[1] + 8, o[2]:o[2] + 8] += wmap * logits[j]
+    assert torch.equal(acc, ref)
+    with pytest.raises(RuntimeError):
+        ops.blend_accumulate(logits, acc, prof, [(0, 0, 0), (8, 2, 6), (2, 1, 3)])
+    # labels: bit-exact against the oracle's post-processing
+    prob_sum = torch.rand((3, 12, 10, 14), device=DEV, generator=g) * 8
+    img = vol[0].clone()
+    img[:, :3] = 0
+    onehot, label = ops.labels_finalize(prob_sum, 8, 0.5, image=img)
+    hard = ((prob_sum / 8) >= 0.5).float()[None].cpu()
+    hard = oinf.remove_background_voxels(img[None].cpu(), hard)
+    assert torch.equal(onehot.cpu().float()[None], hard)
+    assert torch.equal(label.cpu()[None, None], oinf.brats_label_map(hard))
