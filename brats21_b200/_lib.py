@@ -22,6 +22,10 @@ _SIGNATURES = {
     "b21_conv_cout_padded": [_i],
     "b21_pack_conv_weight": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b21_conv3d_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv_march_supported": [_i, _i],
+    "b21_conv_march_weight_bytes": [_i, _i],
+    "b21_pack_conv_weight_march": [_vp, _vp, _i, _i, _i, _vp],
+    "b21_conv3d_march_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _vp],
     "b21_se_gate": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "b21_scale_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -60,6 +64,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _i
+    lib.b21_conv_march_weight_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 

@@ -1,0 +1,433 @@
+// conv_march.cu — "plane-marching" implicit-GEMM conv3d (k = 3, dilation 1, stride 1) for sm_100a.
+//
+// The tap-streaming kernel (conv_tap.cu) re-fetches its activation tile from L2 once per tap (27x), which makes the
+// small-channel layers that hold most of the FLOPs (48 -> 48 at full resolution) L2-bandwidth bound, and with
+// N = Cout = 48 every tcgen05.mma spends more cycles reading its 4 KB A tile from shared memory than multiplying.
+// This kernel removes both limits:
+//
+//   * One persistent CTA per SM owns an (h, w) tile of 16 x 8 output voxels (M = 128) and MARCHES along d.  Each
+//     input plane (18 x 10 halo, all channels) is brought into shared memory exactly once by TMA (out-of-bounds
+//     zero fill = the convolution's zero padding) and serves all 27 taps: a tap is just a different start address
+//     of the UMMA shared-memory descriptor.  The plane is stored channel-chunk-major ([Cin/8][18][10][8 ch],
+//     SWIZZLE_NONE "interleaved" K-major core matrices: 8 consecutive w voxels x 16 B = one 128 B core matrix), so
+//     arbitrary (kh, kw) shifts keep the canonical layout: SBO = 160 B (next h row), LBO = 2944 B (next 8 channels).
+//   * All 27 x Cin x Cout weights stay resident in shared memory (loaded once per CTA with cp.async.bulk).
+//   * The three kd taps are folded into the N dimension: for input plane d' the MMA computes, per (kh, kw),
+//     D[128, 3*Cout] += A[128, Cin] * [W(kd=2) | W(kd=1) | W(kd=0)], whose three column groups belong to output
+//     planes d'-1, d', d'+1.  TMEM holds a ring of per-output-plane accumulators (Cout fp32 columns each); the three
+//     groups are adjacent ring slots.  N = 144 instead of 48 amortises the A-tile read over 3x the math.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (tcgen05.ld ->
+//     + bias -> GroupNorm/EvoNorm group statistics -> bf16 NDHWC store) overlapped with the MMAs of later planes.
+//
+// Replaces torch.nn.Conv3d(k=3, padding=1) at networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201
+// for the layers whose weights fit in shared memory (54 * ceil16(Cin) * Cout bytes); other shapes use conv_tap.cu.
+#include "ptx.cuh"
+#include "host_common.h"
+#include <stdlib.h>
+
+namespace b21 {
+
+constexpr int kMThreads = 192;
+constexpr int kMTH = 16, kMTW = 8;                // in-plane output tile: M = 128 rows = 16 h x 8 w
+constexpr int kMHH = kMTH + 2, kMHW = kMTW + 2;   // halo plane 18 x 10
+constexpr int kMChunkData = kMHH * kMHW * 16;     // one 8-channel chunk of a halo plane (2880 B of TMA payload)
+constexpr int kMChunkBytes = (kMChunkData + 127) / 128 * 128;  // chunk stride: TMA destinations are 128 B aligned
+constexpr int kMMaxStages = 6;
+constexpr int kMMaxRing = 16;
+constexpr int kMSmemBudget = 225 * 1024;
+
+struct ConvMarchParams {
+  __nv_bfloat16* y;
+  const uint8_t* wpk;
+  const float* bias;
+  double* stats;
+  int N, D, H, W, ldy;
+  int kc;  // 8-channel chunks per plane (Cin rounded up to 16, divided by 8)
+  int tilesH, tilesW, segs, L, items;
+  int stages, ring;
+  uint32_t wbytes;
+  int variant;  // debug: bit0 swaps LBO/SBO of A, bit1 of B
+};
+
+__device__ __forceinline__ uint64_t nosw_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return umma_smem_desc(saddr, lbo, sbo, kLayoutNone);
+}
+
+struct MarchItem {
+  int n, h0, w0, d0, Lc;
+};
+__device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int item) {
+  MarchItem it;
+  int t = item;
+  const int wt = t % p.tilesW; t /= p.tilesW;
+  const int ht = t % p.tilesH; t /= p.tilesH;
+  const int sg = t % p.segs;
+  it.n = t / p.segs;
+  it.h0 = ht * kMTH;
+  it.w0 = wt * kMTW;
+  it.d0 = sg * p.L;
+  it.Lc = p.D - it.d0 < p.L ? p.D - it.d0 : p.L;
+  return it;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kMThreads, 1)
+conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMMaxStages];
+  __shared__ __align__(8) uint64_t accf_bar[kMMaxRing];
+  __shared__ __align__(8) uint64_t acce_bar[kMMaxRing];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_stat[2][16];
+  __shared__ float s_bias[COUT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_p = smem + ((p.wbytes + 127u) & ~127u);
+  const uint32_t plane_bytes = uint32_t(p.kc) * kMChunkBytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int r = 0; r < p.ring; ++r) {
+      mbar_init(&accf_bar[r], 1);
+      mbar_init(&acce_bar[r], 4);
+    }
+    mbar_init(&w_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+  }
+  if (threadIdx.x < 32) s_stat[threadIdx.x >> 4][threadIdx.x & 15] = 0.f;
+  for (int c = threadIdx.x; c < COUT; c += kMThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: weights once, then planes
+    if (lane == 0) {
+      mbar_expect_tx(&w_bar, p.wbytes);
+      for (uint32_t off = 0; off < p.wbytes; off += 16384u) {
+        const uint32_t nb = p.wbytes - off < 16384u ? p.wbytes - off : 16384u;
+        bulk_load_1d(smem_w + off, p.wpk + off, nb, &w_bar);
+      }
+      uint32_t pc = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const MarchItem it = decode_item(p, item);
+        for (int i = 0; i <= it.Lc + 1; ++i) {
+          const int dz = it.d0 - 1 + i;
+          if (dz < 0 || dz >= p.D) continue;
+          const int s = pc % p.stages;
+          const uint32_t ph = (pc / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* dst = smem_p + size_t(s) * plane_bytes;
+          mbar_expect_tx(&full_bar[s], uint32_t(p.kc) * kMChunkData);
+          for (int c = 0; c < p.kc; ++c)
+            tma_load_5d(dst + c * kMChunkBytes, &tmX, &full_bar[s], c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
+          ++pc;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t lboB = (3 * COUT / 8) * 128, sboB = 128;
+      constexpr uint32_t lboA = kMChunkBytes, sboA = kMHW * 16;
+      const uint32_t tap_bytes = uint32_t(p.kc) * lboB;
+      const uint64_t dA = (p.variant & 1) ? nosw_desc(0, sboA, lboA) : nosw_desc(0, lboA, sboA);
+      const uint64_t dB = (p.variant & 2) ? nosw_desc(0, sboB, lboB) : nosw_desc(0, lboB, sboB);
+      const uint32_t idesc1 = umma_idesc_bf16(128, COUT), idesc2 = umma_idesc_bf16(128, 2 * COUT),
+                     idesc3 = umma_idesc_bf16(128, 3 * COUT);
+      const uint32_t w_addr = smem_u32(smem_w);
+      const int ksteps = p.kc >> 1;
+      mbar_wait(&w_bar, 0);
+      tc_fence_after();
+      uint32_t pc = 0, sg_base = 0, next_fresh = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const MarchItem it = decode_item(p, item);
+        for (int i = 0; i <= it.Lc + 1; ++i) {
+          const int dz = it.d0 - 1 + i;
+          if (dz < 0 || dz >= p.D) continue;
+          const int s = pc % p.stages;
+          const uint32_t ph = (pc / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j
+          const int jlo = i >= 2 ? 0 : 2 - i;
+          const int jhi = i + 1 <= it.Lc ? 2 : it.Lc + 1 - i;
+          const uint32_t a_addr = smem_u32(smem_p + size_t(s) * plane_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t aa = a_addr + uint32_t(kh * kMHW + kw) * 16u + uint32_t(ks) * 2u * lboA;
+              const uint64_t ad = dA | uint64_t((aa & 0x3FFFF) >> 4);
+              const uint32_t bb = w_addr + uint32_t(tap) * tap_bytes + uint32_t(ks) * 2u * lboB;
+              const bool first = (tap | ks) == 0;
+              int j = jlo;
+              while (j <= jhi) {
+                const uint32_t sg = sg_base + uint32_t(i + j - 2);
+                const uint32_t r = sg % uint32_t(p.ring);
+                const uint32_t bj = bb + uint32_t(j) * (COUT / 8) * 128u;
+                const uint64_t bd = dB | uint64_t((bj & 0x3FFFF) >> 4);
+                if (first) {
+                  uint32_t acc = 1;
+                  if (sg >= next_fresh) {  // first contribution to this output plane: claim the ring slot
+                    mbar_wait(&acce_bar[r], ((sg / uint32_t(p.ring)) & 1) ^ 1);
+                    tc_fence_after();
+                    acc = 0;
+                    next_fresh = sg + 1;
+                  }
+                  umma_bf16(tmem_base + r * COUT, ad, bd, idesc1, acc);
+                  ++j;
+                } else {
+                  int len = jhi - j + 1;
+                  const int room = p.ring - int(r);
+                  len = len < room ? len : room;
+                  umma_bf16(tmem_base + r * COUT, ad, bd, len == 3 ? idesc3 : (len == 2 ? idesc2 : idesc1), 1u);
+                  j += len;
+                }
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (i >= 2) umma_commit(&accf_bar[(sg_base + uint32_t(i - 2)) % uint32_t(p.ring)]);  // plane so = i-1 done
+          if (i == it.Lc && it.d0 + it.Lc >= p.D)                                               // no plane i+1 exists
+            umma_commit(&accf_bar[(sg_base + uint32_t(i - 1)) % uint32_t(p.ring)]);
+          ++pc;
+        }
+        sg_base += uint32_t(it.Lc);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int hh = row >> 3, ww = row & 7;
+    constexpr int GS = COUT / 8;  // channels per norm group
+    uint32_t og = 0;
+    int buf = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const MarchItem it = decode_item(p, item);
+      const int h = it.h0 + hh, w = it.w0 + ww;
+      const bool valid = (h < p.H) && (w < p.W);
+      float gs[8], gq[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+      for (int so = 0; so < it.Lc; ++so, ++og) {
+        const uint32_t r = og % uint32_t(p.ring);
+        mbar_wait(&accf_bar[r], (og / uint32_t(p.ring)) & 1);
+        tc_fence_after();
+        float v[COUT];
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16)
+          tmem_ld16(tmem_base + (uint32_t(quad * 32) << 16) + r * COUT + uint32_t(c0), v + c0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acce_bar[r]);  // slot may be overwritten: values are in registers now
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float val = v[c] + s_bias[c];
+          v[c] = val;
+          const float sv = valid ? val : 0.f;
+          gs[c / GS] += sv;
+          gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+        }
+        if (valid) {
+          const size_t vox = ((size_t(it.n) * p.D + (it.d0 + so)) * p.H + h) * p.W + w;
+          __nv_bfloat16* yrow = p.y + vox * size_t(p.ldy);
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
+            o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
+            o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
+            o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
+            *reinterpret_cast<uint4*>(yrow + c0) = o;
+          }
+        }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float a = warp_sum(gs[g]), b = warp_sum(gq[g]);
+          if (lane == 0) {
+            atomicAdd(&s_stat[buf][g * 2], a);
+            atomicAdd(&s_stat[buf][g * 2 + 1], b);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+        if (warp == 2 && lane < 16) {
+          const float sv = s_stat[buf][lane];
+          s_stat[buf][lane] = 0.f;
+          if (sv != 0.f) {
+            const int slot = item % B21_STAT_SLOTS;
+            atomicAdd(p.stats + ((size_t(slot) * p.N + it.n) * 8) * 2 + lane, double(sv));
+          }
+        }
+        buf ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ weight repack
+// out = shared-memory image: [tap9 = kh*3+kw][kc][ng = 3*cout/8][8 n][8 k] bf16, n = j*cout + co with kd = 2 - j.
+__global__ void pack_march_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
+                                         int cin_o, int rows, int kc, int transpose_flip) {
+  const int ng = 3 * rows / 8;
+  const size_t total = size_t(9) * kc * ng * 64;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
+    size_t t = i >> 6;
+    const int g = int(t % ng); t /= ng;
+    const int c = int(t % kc);
+    const int tap9 = int(t / kc);
+    const int n = g * 8 + n8, j = n / rows, ro = n % rows, kd = 2 - j, kh = tap9 / 3, kw = tap9 % 3;
+    const int ki = c * 8 + k8;
+    float v = 0.f;
+    if (!transpose_flip) {
+      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + (kd * 9 + kh * 3 + kw)];
+    } else {
+      // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
+      if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + ((2 - kd) * 9 + (2 - kh) * 3 + (2 - kw))];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int march_kc(int cin) { return (cin + 15) / 16 * 2; }
+static inline size_t march_wbytes(int cin, int cout) { return size_t(9) * march_kc(cin) * (3 * cout / 8) * 128; }
+
+static int march_stages(int cin, int cout) {
+  const size_t wb = (march_wbytes(cin, cout) + 127) & ~size_t(127);
+  const size_t plane = size_t(march_kc(cin)) * kMChunkBytes;
+  if (wb + 128 >= size_t(kMSmemBudget)) return 0;
+  size_t st = (size_t(kMSmemBudget) - wb - 128) / plane;
+  return int(st > kMMaxStages ? kMMaxStages : st);
+}
+
+}  // namespace b21
+
+using namespace b21;
+
+extern "C" int b21_conv_march_supported(int cin, int cout) {
+  if (!(cout == 16 || cout == 32 || cout == 48 || cout == 64)) return 0;
+  if (cin <= 0 || cin % 8) return 0;
+  return march_stages(cin, cout) >= 3 ? 1 : 0;
+}
+
+extern "C" long long b21_conv_march_weight_bytes(int cin, int cout) { return (long long)march_wbytes(cin, cout); }
+
+extern "C" int b21_pack_conv_weight_march(const float* w, void* packed, int cout, int cin, int transpose_flip,
+                                          void* stream) {
+  B21_CHECK_ARG(w && packed, "pack_conv_weight_march: null pointer");
+  const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
+  B21_CHECK_ARG(rows % 8 == 0, "pack_conv_weight_march: output channels %d must be a multiple of 8", rows);
+  const int kc = march_kc(inner);
+  const size_t total = march_wbytes(inner, rows) / 2;
+  const int threads = 256;
+  const int blocks = int((total + threads - 1) / threads) < 2048 ? int((total + threads - 1) / threads) : 2048;
+  pack_march_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, kc, transpose_flip);
+  B21_LAUNCH_CHECK("pack_march_weight_kernel");
+  return B21_OK;
+}
+
+template <int COUT>
+static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kMSmemBudget));
+    attr_set = true;
+  }
+  conv_march_kernel<COUT><<<grid, kMThreads, smem_bytes, stream>>>(tm, p);
+  B21_LAUNCH_CHECK("conv_march_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
+                                    double* stats, int n, int d, int h, int w, int cin, int cout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B21_CHECK_ARG(x && w_march && y, "conv3d_march_fwd: null pointer");
+  B21_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0, "conv3d_march_fwd: bad shape %d %d %d %d", n, d, h, w);
+  B21_CHECK_ARG(b21_conv_march_supported(cin, cout), "conv3d_march_fwd: (cin %d, cout %d) unsupported", cin, cout);
+  B21_CHECK_ARG(ldx >= cin && ldx % 8 == 0 && ldy >= cout && ldy % 8 == 0, "conv3d_march_fwd: bad ldx %d / ldy %d", ldx, ldy);
+  B21_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(w_march) & 15) == 0,
+                "conv3d_march_fwd: pointers must be 16-byte aligned");
+
+  ConvMarchParams p;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.wpk = reinterpret_cast<const uint8_t*>(w_march);
+  p.bias = bias;
+  p.stats = stats;
+  p.N = n; p.D = d; p.H = h; p.W = w; p.ldy = ldy;
+  p.kc = march_kc(cin);
+  p.tilesH = (h + kMTH - 1) / kMTH;
+  p.tilesW = (w + kMTW - 1) / kMTW;
+  p.stages = march_stages(cin, cout);
+  p.ring = 512 / cout < kMMaxRing ? 512 / cout : kMMaxRing;
+  p.wbytes = (uint32_t)march_wbytes(cin, cout);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("B21_MARCH_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  p.variant = variant;
+
+  // march length: the longest segment that still balances the persistent grid (each segment re-reads 2 halo planes)
+  const int sms = num_sms();
+  const long long tiles = (long long)n * p.tilesH * p.tilesW;
+  int bestL = d;
+  double best = -1.0;
+  for (int segs = 1; segs <= d; ++segs) {
+    const int L = (d + segs - 1) / segs;
+    if (L < 8 && segs > 1) break;
+    if ((d + L - 1) / L != segs) continue;
+    const long long items = tiles * segs;
+    const long long rounds = (items + sms - 1) / sms;
+    const double eff = double(items) / double(rounds * sms) * double(L) / double(L + 2);
+    if (eff > best + 1e-9) {
+      best = eff;
+      bestL = L;
+    }
+  }
+  p.L = bestL;
+  p.segs = (d + p.L - 1) / p.L;
+  p.items = int(tiles * p.segs);
+  const int grid = p.items < sms ? p.items : sms;
+
+  CUtensorMap tm;
+  {
+    const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t str[4] = {uint64_t(ldx) * 2, uint64_t(w) * ldx * 2, uint64_t(h) * w * ldx * 2,
+                             uint64_t(d) * h * w * ldx * 2};
+    const uint32_t box[5] = {8, (uint32_t)kMHW, (uint32_t)kMHH, 1, 1};
+    int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
+  if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
+  const size_t smem_bytes = ((size_t(p.wbytes) + 127) & ~size_t(127)) + size_t(p.stages) * p.kc * kMChunkBytes + 128;
+  switch (cout) {
+    case 16: return launch_march<16>(tm, p, smem_bytes, grid, stream);
+    case 32: return launch_march<32>(tm, p, smem_bytes, grid, stream);
+    case 48: return launch_march<48>(tm, p, smem_bytes, grid, stream);
+    default: return launch_march<64>(tm, p, smem_bytes, grid, stream);
+  }
+}

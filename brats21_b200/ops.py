@@ -36,6 +36,14 @@ class PackedConv:
         call("b21_pack_conv_weight", ptr(w32), ptr(self.w), cout, cin, cin_padded, k, int(transpose_flip),
              stream_ptr())
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        # plane-marching packing (k = 3, weights resident in shared memory) when the shape allows it
+        self.w_march = None
+        lib = _lib.load()
+        if k == 3 and lib.b21_conv_march_supported(cin_padded, rows):
+            nbytes = lib.b21_conv_march_weight_bytes(cin_padded, rows)
+            self.w_march = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
+            call("b21_pack_conv_weight_march", ptr(w32), ptr(self.w_march), cout, cin, int(transpose_flip),
+                 stream_ptr())
 
 
 def new_stats(n: int, device) -> torch.Tensor:
@@ -55,8 +63,12 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("b21_conv3d_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
-         n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
+    if use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
+        call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
+             n, d, h, w, cin, pw.cout, stream_ptr())
+    else:
+        call("b21_conv3d_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
+             n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
     if prof is not None:
         e1.record()
         prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (cin, pw.cout, pw.taps, d)))
@@ -66,6 +78,8 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
 # When set to a list, every conv launch appends (start_event, end_event, algorithmic_flops, shape_key):
 # bench.py uses it to time the dominant kernel live with CUDA events on the launching stream.
 conv_profile = None
+# The plane-marching kernel is the default for the shapes it supports; tools flip this to time the tap kernel.
+use_march = True
 
 
 # ---------------------------------------------------------------------------------------------- norm / SE / pool

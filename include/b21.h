@@ -57,6 +57,17 @@ int b21_conv3d_fwd(const void* x, int ldx, const void* w_packed, const float* bi
                    double* stats, int n, int d, int h, int w, int cin, int cout, int taps, int dil,
                    void* stream);
 
+/* Plane-marching variant of b21_conv3d_fwd for k = 3, dilation 1 layers whose weights fit in shared memory
+ * (b21_conv_march_supported): every input plane is read once and serves all 27 taps; the three kd taps are folded
+ * into the MMA N dimension.  Same semantics (bias, stats, channel-slice ld) as b21_conv3d_fwd with taps = 27, dil = 1.
+ * The weight is packed by b21_pack_conv_weight_march into b21_conv_march_weight_bytes(cin, cout) bytes:
+ * bf16 [kh*3+kw][ceil16(cin)/8][3*cout/8][8 n][8 k], n = (2-kd)*cout + co; `transpose_flip` as above. */
+int b21_conv_march_supported(int cin, int cout);
+long long b21_conv_march_weight_bytes(int cin, int cout);
+int b21_pack_conv_weight_march(const float* w, void* packed, int cout, int cin, int transpose_flip, void* stream);
+int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
+                         double* stats, int n, int d, int h, int w, int cin, int cout, void* stream);
+
 /* ------------------------------------------------------------------------------------- normalisation / SE
  * norm_apply: y = GroupNorm(8,C)(x) -> ReLU (mode 0; networks/factory.py:182 + equiunet2020.py:60-61) or
  * EvoNorm3D-S0 (mode 1; networks/equiunet2021.py:48-52,95-105: x*sigmoid(x)/sqrt(var_unbiased+eps)*gamma+beta)

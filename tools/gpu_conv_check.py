@@ -116,24 +116,39 @@ def main():
         ("tiny4", 1, 4, 4, 4, 128, 128, 3, 1),
         ("tiny2", 1, 2, 2, 2, 64, 64, 3, 2),
         ("w16", 1, 32, 32, 32, 16, 16, 3, 1),
+        # plane-marching kernel: several d segments / work items per CTA, ragged tiles, ring wrap-around
+        ("m48_long", 2, 40, 24, 24, 48, 48, 3, 1),
+        ("m48_ragged", 1, 21, 19, 13, 48, 48, 3, 1),
+        ("m32_32", 1, 20, 16, 32, 32, 32, 3, 1),
+        ("m16_64", 1, 9, 32, 16, 16, 64, 3, 1),
+        ("m8_48_d1", 3, 1, 16, 8, 8, 48, 3, 1),
+        ("m48_many", 1, 24, 160, 160, 48, 48, 3, 1),
     ]
+    if "--march-only" in sys.argv:
+        cases = [c for c in cases if c[7] == 3 and c[8] == 1 and c[6] in (16, 32, 48, 64) and c[5] <= 48]
     for c in cases:
         try:
             r = one_case(*c)
+            r["kernel"] = "march" if (ops.use_march and c[7] == 3 and c[8] == 1 and c[6] in (16, 32, 48, 64)
+                                      and c[5] <= 48 and c[3] >= 8 and c[4] >= 8) else "tap"
         except Exception as e:  # noqa: BLE001
-            r = {"case": c[0], "ok": False, "error": repr(e), "tb": traceback.format_exc()[-600:]}
+            r = {"case": c[0], "ok": False, "error": repr(e)[:160]}
         print(r, flush=True)
         out["correctness"].append(r)
+        if "error" in r and "CUDA error" in r["error"]:
+            break  # the context is gone; later cases would only repeat the error
     try:
         r = one_case("slices", 1, 8, 8, 8, 48, 24, 1, 1, ldx=96, ldy=48)
     except Exception as e:  # noqa: BLE001
-        r = {"case": "slices", "ok": False, "error": repr(e)}
+        r = {"case": "slices", "ok": False, "error": repr(e)[:160]}
     print(r, flush=True)
     out["correctness"].append(r)
 
     if "--perf" in sys.argv:
         perf = [
             ("L1_48_48_b4", 4, 128, 48, 48, 3, 1),
+            ("L1_8_48_b4", 4, 128, 8, 48, 3, 1),
+            ("L1_48_48_b1", 1, 128, 48, 48, 3, 1),
             ("L1_96_48_b4", 4, 128, 96, 48, 3, 1),
             ("L2_96_96_b4", 4, 64, 96, 96, 3, 1),
             ("L3_192_192_b4", 4, 32, 192, 192, 3, 1),
@@ -143,8 +158,12 @@ def main():
         for c in perf:
             try:
                 r = perf_case(*c)
+                if c[5] == 3 and c[4] in (16, 32, 48, 64) and c[3] <= 48:  # also time the tap kernel on these
+                    ops.use_march = False
+                    r["tap_ms"] = perf_case(*c)["ms"]
+                    ops.use_march = True
             except Exception as e:  # noqa: BLE001
-                r = {"case": c[0], "error": repr(e)}
+                r = {"case": c[0], "error": repr(e)[:160]}
             print(r, flush=True)
             out["perf"].append(r)
     os.makedirs("gpurun_out", exist_ok=True)
@@ -154,6 +173,8 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--no-march" in sys.argv:
+        ops.use_march = False
     t0 = time.time()
     main()
     print("elapsed", time.time() - t0)
