@@ -46,7 +46,7 @@ struct ConvMarchParams {
   int tilesH, tilesW, segs, L, items;
   int stages, ring;
   uint32_t wbytes;
-  int variant;  // debug: bit0 swaps LBO/SBO of A, bit1 of B
+  int variant;  // debug (B21_MARCH_VARIANT): bit2 no TMA loads, bit3 no stores, bit4 three taps only, bit5 no epilogue math/stores, bit6 no TMEM ld/st
 };
 
 __device__ __forceinline__ uint64_t nosw_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -73,6 +73,7 @@ __device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int i
 template <int COUT>
 __global__ void __launch_bounds__(kMThreads, 1)
 conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams p) {
+  constexpr uint32_t RING = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;  // accumulator slots in TMEM
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMMaxStages];
@@ -85,16 +86,18 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* smem_w = smem;
-  uint8_t* smem_p = smem + ((p.wbytes + 127u) & ~127u);
+  const uint32_t w_addr = smem_u32(smem);
+  const uint32_t p_addr = w_addr + ((p.wbytes + 127u) & ~127u);
   const uint32_t plane_bytes = uint32_t(p.kc) * kMChunkBytes;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t accf0 = smem_u32(&accf_bar[0]), acce0 = smem_u32(&acce_bar[0]);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int r = 0; r < p.ring; ++r) {
+    for (uint32_t r = 0; r < RING; ++r) {
       mbar_init(&accf_bar[r], 1);
       mbar_init(&acce_bar[r], 4);
     }
@@ -115,97 +118,122 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: weights once, then planes
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&w_bar, p.wbytes);
       for (uint32_t off = 0; off < p.wbytes; off += 16384u) {
         const uint32_t nb = p.wbytes - off < 16384u ? p.wbytes - off : 16384u;
-        bulk_load_1d(smem_w + off, p.wpk + off, nb, &w_bar);
+        bulk_load_1d(smem + off, p.wpk + off, nb, &w_bar);
       }
-      uint32_t pc = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = uint32_t(p.kc) * kMChunkData;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const MarchItem it = decode_item(p, item);
         for (int i = 0; i <= it.Lc + 1; ++i) {
           const int dz = it.d0 - 1 + i;
           if (dz < 0 || dz >= p.D) continue;
-          const int s = pc % p.stages;
-          const uint32_t ph = (pc / p.stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* dst = smem_p + size_t(s) * plane_bytes;
-          mbar_expect_tx(&full_bar[s], uint32_t(p.kc) * kMChunkData);
-          for (int c = 0; c < p.kc; ++c)
-            tma_load_5d(dst + c * kMChunkBytes, &tmX, &full_bar[s], c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
-          ++pc;
+          mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+          const uint32_t fb = full0 + 8u * stage;
+          if (p.variant & 4) {  // debug: no loads
+            mbar_arrive_a(fb);
+          } else {
+            const uint32_t dst = p_addr + uint32_t(stage) * plane_bytes;
+            mbar_expect_tx_a(fb, tx);
+            for (int c = 0; c < p.kc; ++c)
+              tma_load_5d_a(dst + c * kMChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
       constexpr uint32_t lboB = (3 * COUT / 8) * 128, sboB = 128;
       constexpr uint32_t lboA = kMChunkBytes, sboA = kMHW * 16;
-      const uint32_t tap_bytes = uint32_t(p.kc) * lboB;
-      const uint64_t dA = (p.variant & 1) ? nosw_desc(0, sboA, lboA) : nosw_desc(0, lboA, sboA);
-      const uint64_t dB = (p.variant & 2) ? nosw_desc(0, sboB, lboB) : nosw_desc(0, lboB, sboB);
+      const uint64_t dA = nosw_desc(0, lboA, sboA), dB = nosw_desc(0, lboB, sboB);
       const uint32_t idesc1 = umma_idesc_bf16(128, COUT), idesc2 = umma_idesc_bf16(128, 2 * COUT),
                      idesc3 = umma_idesc_bf16(128, 3 * COUT);
-      const uint32_t w_addr = smem_u32(smem_w);
+      const uint64_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);
+      const uint64_t bd0 = dB + uint64_t(w_addr >> 4);
       const int ksteps = p.kc >> 1;
+      const int nkh = (p.variant & 16) ? 1 : 3;
       mbar_wait(&w_bar, 0);
       tc_fence_after();
-      uint32_t pc = 0, sg_base = 0, next_fresh = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const MarchItem it = decode_item(p, item);
+        uint32_t r_lo = r_base;
         for (int i = 0; i <= it.Lc + 1; ++i) {
+          // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j; the lowest valid
+          // group of plane i sits in ring slot r_lo, which advances by one per plane once i >= 3.
+          if (i >= 3) r_lo = r_lo + 1 == RING ? 0 : r_lo + 1;
           const int dz = it.d0 - 1 + i;
           if (dz < 0 || dz >= p.D) continue;
-          const int s = pc % p.stages;
-          const uint32_t ph = (pc / p.stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j
           const int jlo = i >= 2 ? 0 : 2 - i;
           const int jhi = i + 1 <= it.Lc ? 2 : it.Lc + 1 - i;
-          const uint32_t a_addr = smem_u32(smem_p + size_t(s) * plane_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t aa = a_addr + uint32_t(kh * kMHW + kw) * 16u + uint32_t(ks) * 2u * lboA;
-              const uint64_t ad = dA | uint64_t((aa & 0x3FFFF) >> 4);
-              const uint32_t bb = w_addr + uint32_t(tap) * tap_bytes + uint32_t(ks) * 2u * lboB;
-              const bool first = (tap | ks) == 0;
-              int j = jlo;
-              while (j <= jhi) {
-                const uint32_t sg = sg_base + uint32_t(i + j - 2);
-                const uint32_t r = sg % uint32_t(p.ring);
-                const uint32_t bj = bb + uint32_t(j) * (COUT / 8) * 128u;
-                const uint64_t bd = dB | uint64_t((bj & 0x3FFFF) >> 4);
-                if (first) {
-                  uint32_t acc = 1;
-                  if (sg >= next_fresh) {  // first contribution to this output plane: claim the ring slot
-                    mbar_wait(&acce_bar[r], ((sg / uint32_t(p.ring)) & 1) ^ 1);
-                    tc_fence_after();
-                    acc = 0;
-                    next_fresh = sg + 1;
-                  }
-                  umma_bf16(tmem_base + r * COUT, ad, bd, idesc1, acc);
-                  ++j;
-                } else {
-                  int len = jhi - j + 1;
-                  const int room = p.ring - int(r);
-                  len = len < room ? len : room;
-                  umma_bf16(tmem_base + r * COUT, ad, bd, len == 3 ? idesc3 : (len == 2 ? idesc2 : idesc1), 1u);
-                  j += len;
+          const int ngroups = jhi - jlo + 1;
+          const uint32_t sg_lo = sg_base + uint32_t(i + jlo - 2);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint32_t sg = sg_lo + uint32_t(g);
+            if (g < ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
+              uint32_t r = r_lo + uint32_t(g);
+              r = r >= RING ? r - RING : r;
+              mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
+              claim_par ^= 1u << r;
+              next_fresh = sg + 1;
+            }
+          }
+          mbar_wait_a(full0 + 8u * stage, phase);
+          tc_fence_after();
+          const int room = int(RING - r_lo);
+          const int len0 = ngroups < room ? ngroups : room, len1 = ngroups - len0;  // at most one ring wrap
+          const uint32_t col0 = tmem_base + r_lo * COUT, col1 = tmem_base;
+          const uint32_t id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
+          const uint32_t id1 = len1 == 2 ? idesc2 : idesc1;
+          uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
+          uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
+          if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
+            for (int kh = 0; kh < nkh; ++kh, a_row += kMHW) {
+              uint64_t a_tap = a_row;
+              for (int kw = 0; kw < 3; ++kw, ++a_tap) {
+                uint64_t ad = a_tap;
+                for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) umma_bf16(col0, ad, bq, id0, 1u);
+              }
+            }
+          } else {
+            const uint64_t b1 = uint64_t(len0) * COUT;
+            for (int kh = 0; kh < nkh; ++kh, a_row += kMHW) {
+              uint64_t a_tap = a_row;
+              for (int kw = 0; kw < 3; ++kw, ++a_tap) {
+                uint64_t ad = a_tap;
+                for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
+                  umma_bf16(col0, ad, bq, id0, 1u);
+                  umma_bf16(col1, ad, bq + b1, id1, 1u);
                 }
               }
             }
           }
-          umma_commit(&empty_bar[s]);
-          if (i >= 2) umma_commit(&accf_bar[(sg_base + uint32_t(i - 2)) % uint32_t(p.ring)]);  // plane so = i-1 done
-          if (i == it.Lc && it.d0 + it.Lc >= p.D)                                               // no plane i+1 exists
-            umma_commit(&accf_bar[(sg_base + uint32_t(i - 1)) % uint32_t(p.ring)]);
-          ++pc;
+          umma_commit_a(empty0 + 8u * stage);
+          if (i >= 2) umma_commit_a(accf0 + 8u * r_lo);  // output plane so = i - 1 is complete
+          if (i == it.Lc && it.d0 + it.Lc >= p.D) {       // no plane i + 1 exists: so = i is complete as well
+            uint32_t r = r_lo + uint32_t(1 - jlo);
+            r = r >= RING ? r - RING : r;
+            umma_commit_a(accf0 + 8u * r);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
         sg_base += uint32_t(it.Lc);
+        r_base = (r_base + uint32_t(it.Lc)) % RING;
       }
     }
   } else {
@@ -213,8 +241,16 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
+    const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
     constexpr int GS = COUT / 8;  // channels per norm group
-    uint32_t og = 0;
+    // accumulators start at zero and are re-zeroed after every drain: the MMAs always accumulate
+    for (uint32_t c0 = 0; c0 < RING * COUT; c0 += 16) tmem_st16_zero(tlane + c0);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (uint32_t r = 0; r < RING; ++r) mbar_arrive_a(acce0 + 8u * r);
+    uint32_t r = 0, use_par = 0;
     int buf = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const MarchItem it = decode_item(p, item);
@@ -223,18 +259,29 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       float gs[8], gq[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
-      for (int so = 0; so < it.Lc; ++so, ++og) {
-        const uint32_t r = og % uint32_t(p.ring);
-        mbar_wait(&accf_bar[r], (og / uint32_t(p.ring)) & 1);
+      __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy);
+      const size_t ystep = size_t(p.H) * p.W * p.ldy;
+      for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
+        mbar_wait_a(accf0 + 8u * r, (use_par >> r) & 1u);
+        use_par ^= 1u << r;
         tc_fence_after();
         float v[COUT];
+        if (!(p.variant & 64)) {
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 16)
-          tmem_ld16(tmem_base + (uint32_t(quad * 32) << 16) + r * COUT + uint32_t(c0), v + c0);
-        tmem_ld_wait();
+          for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tlane + r * COUT + uint32_t(c0), v + c0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16_zero(tlane + r * COUT + uint32_t(c0));
+          tmem_st_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) v[c] = 0.f;
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acce_bar[r]);  // slot may be overwritten: values are in registers now
+        if (lane == 0) mbar_arrive_a(acce0 + 8u * r);  // slot drained + zeroed: the MMA warp may reuse it
+        r = r + 1 == RING ? 0 : r + 1;
+        if (p.variant & 32) continue;  // debug: handshake only
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
           const float val = v[c] + s_bias[c];
@@ -243,9 +290,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
           gs[c / GS] += sv;
           gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
         }
-        if (valid) {
-          const size_t vox = ((size_t(it.n) * p.D + (it.d0 + so)) * p.H + h) * p.W + w;
-          __nv_bfloat16* yrow = p.y + vox * size_t(p.ldy);
+        if (valid && !(p.variant & 8)) {
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 8) {
             uint4 o;

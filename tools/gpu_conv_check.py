@@ -144,6 +144,9 @@ def main():
     print(r, flush=True)
     out["correctness"].append(r)
 
+    if "--perf1" in sys.argv:
+        print(perf_case("L1_48_48_b4", 4, 128, 48, 48, 3, 1), flush=True)
+        return
     if "--perf" in sys.argv:
         perf = [
             ("L1_48_48_b4", 4, 128, 48, 48, 3, 1),
