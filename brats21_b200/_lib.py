@@ -36,6 +36,18 @@ _SIGNATURES = {
     "b21_blend_accumulate": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b21_tta_accumulate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp],
     "b21_labels_finalize": [_vp, _f, _f, _vp, _i, _vp, _vp, _i64, _i, _vp],
+    "b21_conv3d_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_norm_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                     _vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _f, _vp],
+    "b21_pool_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_upsample2x_bwd": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_upsample_f32_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b21_head_conv_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "b21_add_inplace": [_vp, _i, _vp, _i, _i64, _i, _vp],
+    "b21_dice_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _vp],
+    "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp],
+    "b21_ranger_chunk": [],
+    "b21_ranger_step": [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
 }
 
 _lib = None
@@ -87,7 +99,7 @@ def stream_ptr():
 
 
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
-_LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv3d_fwd": 1}
+_LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
 launch_count = 0
 
 

@@ -107,6 +107,23 @@ class _B21Net(nn.Module):
         self._pack_key = None
         self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self.skip_deep_heads_in_eval = False  # set by the inference wrappers (they discard the deep heads)
+        self._gs = None  # flat gradient store of the training path (brats21_b200.autograd.GradStore)
+
+    # ---- training path (brats21_b200/autograd.py)
+    def grad_store(self):
+        if self._gs is None:
+            from .autograd import GradStore
+            self._gs = GradStore(self, self._grad_order())
+        return self._gs
+
+    def _grad_order(self):
+        raise NotImplementedError(f"{type(self).__name__}: training is not on the accelerated path yet")
+
+    def _forward_train(self, x8, want_deep):
+        raise NotImplementedError(f"{type(self).__name__}: training is not on the accelerated path yet")
+
+    def _backward_train(self, tape, dout, ddeeps, gs):
+        raise NotImplementedError(f"{type(self).__name__}: training is not on the accelerated path yet")
 
     # ---- packing
     def _param_key(self):
@@ -353,6 +370,18 @@ class EquiUnetASSPEvo(_B21Net):
             m = self.get_submodule(name)
             self._mat(name + ".w", m.weight)
             self._vec(name + ".bias", m.bias)
+
+    def _grad_order(self):
+        from .autograd import v2_grad_order
+        return v2_grad_order(self)
+
+    def _forward_train(self, x8, want_deep):
+        from .autograd import _v2_forward_train
+        return _v2_forward_train(self, x8, want_deep)
+
+    def _backward_train(self, tape, dout, ddeeps, gs):
+        from .autograd import _backward_v2
+        return _backward_v2(self, tape, dout, ddeeps, gs)
 
     def _block(self, name, x, tmp, out, stats, csum):
         """conv-evo-conv-evo + SE gate; returns (pre-scale activations in `out`, scale [N, C])."""

@@ -193,3 +193,102 @@ def labels_finalize(prob_sum, count, thresh=0.5, image=None, want_onehot=True, w
     call("b21_labels_finalize", ptr(prob_sum), float(count), float(thresh), ptr(image), ic, ptr(onehot), ptr(label),
          nvox, et_label, stream_ptr())
     return onehot, label
+
+
+# ---------------------------------------------------------------------------------------------- training step
+def _ld4(t: torch.Tensor) -> int:
+    return _ld(t)
+
+
+def conv3d_wgrad(x, dz, dw, dil: int = 1):
+    """dw (fp32 [cout, cin, k, k, k], contiguous) += weight gradient of conv3d(x) given dz = d(out)."""
+    n, d, h, w, cin = x.shape
+    cout = dz.shape[-1]
+    k = dw.shape[2]
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == cout and dw.shape[1] <= cin
+    if dw.shape[1] != cin:  # input channels were zero-padded for the forward pass (first layer): use a padded scratch
+        tmp = torch.zeros((cout, cin) + tuple(dw.shape[2:]), dtype=torch.float32, device=dw.device)
+        call("b21_conv3d_wgrad", ptr(x), _ld(x), ptr(dz), _ld(dz), ptr(tmp), n, d, h, w, cin, cout, k ** 3, dil,
+             stream_ptr())
+        dw += tmp[:, :dw.shape[1]]
+        return dw
+    call("b21_conv3d_wgrad", ptr(x), _ld(x), ptr(dz), _ld(dz), ptr(dw), n, d, h, w, cin, cout, k ** 3, dil, stream_ptr())
+    return dw
+
+
+def norm_bwd_workspace(n, c, device):
+    return torch.empty((n * c * 48,), dtype=torch.uint8, device=device)
+
+
+def norm_bwd(dy, z, dz, stats, gamma, beta, dgamma, dbeta, mode, colsum=None, se=None, workspace=None, eps=1e-5):
+    """Backward of norm_apply (+ optional squeeze-excite gate).  se = dict(scale, mean, w1, b1, w2, b2, dw1, db1, dw2,
+    db2) with fp32 contiguous tensors.  Accumulates dgamma/dbeta/colsum/SE grads; writes dz (may alias dy)."""
+    n, d, h, w, c = z.shape
+    if workspace is None:
+        workspace = norm_bwd_workspace(n, c, z.device)
+    s = se or {}
+    call("b21_norm_bwd", ptr(dy), _ld(dy), ptr(z), _ld(z), ptr(dz), _ld(dz), ptr(stats), ptr(gamma), ptr(beta),
+         ptr(dgamma), ptr(dbeta), ptr(colsum), ptr(s.get("scale")), ptr(s.get("mean")), ptr(s.get("w1")),
+         ptr(s.get("b1")), ptr(s.get("w2")), ptr(s.get("b2")), ptr(s.get("dw1")), ptr(s.get("db1")), ptr(s.get("dw2")),
+         ptr(s.get("db2")), s["w1"].shape[0] if se else 0, ptr(workspace), workspace.numel(), mode, n, d * h * w, c, eps,
+         stream_ptr())
+    return dz
+
+
+def pool_bwd(y, dpool, dy, mode, add=None):
+    n, d, h, w, c = y.shape
+    call("b21_pool_bwd", ptr(y), _ld(y), ptr(dpool), _ld(dpool), ptr(add), _ld(add) if add is not None else 0, ptr(dy),
+         _ld(dy), mode, n, d, h, w, c, stream_ptr())
+    return dy
+
+
+def upsample2x_bwd(dy, dx):
+    n, d, h, w, c = dx.shape
+    assert dy.shape == (n, 2 * d, 2 * h, 2 * w, c)
+    call("b21_upsample2x_bwd", ptr(dy), _ld(dy), ptr(dx), _ld(dx), n, d, h, w, c, stream_ptr())
+    return dx
+
+
+def upsample_f32_bwd(dy, s):
+    n, k, do, ho, wo = dy.shape
+    d, h, w = do // s, ho // s, wo // s
+    dx = torch.empty((n, k, d, h, w), dtype=torch.float32, device=dy.device)
+    call("b21_upsample_f32_bwd", ptr(dy.contiguous()), ptr(dx), n * k, d, h, w, s, stream_ptr())
+    return dx
+
+
+def head_conv_bwd(x, weight, dl, dx, scale=None, accumulate=False):
+    """Returns (dws [n, k, c], db [k]); writes/accumulates dx (bf16)."""
+    n, d, h, w, c = x.shape
+    k = weight.shape[0]
+    dws = torch.zeros((n, k, c), dtype=torch.float32, device=x.device)
+    db = torch.zeros((k,), dtype=torch.float32, device=x.device)
+    call("b21_head_conv_bwd", ptr(x), _ld(x), ptr(scale), ptr(weight), ptr(dl.contiguous()), ptr(dx), _ld(dx),
+         int(accumulate), ptr(dws), ptr(db), n, d * h * w, c, k, stream_ptr())
+    return dws, db
+
+
+def add_inplace(dst, src):
+    n, d, h, w, c = dst.shape
+    assert src.shape == dst.shape
+    call("b21_add_inplace", ptr(dst), _ld(dst), ptr(src), _ld(src), n * d * h * w, c, stream_ptr())
+    return dst
+
+
+def dice_fwd(logits, target, loss, jaccard=False, weight=1.0, smooth_nr=1e-5, smooth_dr=1e-5):
+    """loss[0] += weight * DiceLoss(logits, target); returns the coefficient table for dice_bwd."""
+    n, k = logits.shape[:2]
+    nvox = logits[0, 0].numel()
+    sums = torch.empty((k, 3), dtype=torch.float64, device=logits.device)
+    coef = torch.empty((k, 2), dtype=torch.float32, device=logits.device)
+    call("b21_dice_fwd", ptr(logits), ptr(target), ptr(sums), ptr(loss), ptr(coef), n, k, nvox, int(jaccard),
+         smooth_nr, smooth_dr, weight, stream_ptr())
+    return coef
+
+
+def dice_bwd(logits, target, coef, gout=None, gscale=1.0):
+    n, k = logits.shape[:2]
+    dl = torch.empty_like(logits)
+    call("b21_dice_bwd", ptr(logits), ptr(target), ptr(coef), ptr(gout), gscale, ptr(dl), n, k, logits[0, 0].numel(),
+         stream_ptr())
+    return dl

@@ -130,6 +130,64 @@ int b21_tta_accumulate(const float* acc, const float* cnt, float* prob_sum, int 
 int b21_labels_finalize(const float* prob_sum, float count, float thresh, const float* image, int image_channels,
                         uint8_t* onehot, uint8_t* label, long long nvox, int et_label, void* stream);
 
+/* ------------------------------------------------------------------------------------------- training step
+ * Backward of the network body and the criterion (learning/engine.py:88-130: forward, Dice over the heads,
+ * scaler.scale(loss).backward(), optimizer step).  Gradients of activations are ndhwc bf16; gradients of
+ * parameters are fp32 and ACCUMULATED into the buffers passed (zero them at the start of a step).
+ */
+
+/* dW[cout][cin][taps] (fp32, torch Conv3d weight layout) += sum_v dz[v][co] * x[v + off(tap)][ci]: weight gradient
+ * of b21_conv3d_fwd (same x / taps / dil; dz is the gradient of its output).  The data gradient is b21_conv3d_fwd
+ * itself on dz with the `transpose_flip` packing of the weight. */
+int b21_conv3d_wgrad(const void* x, int ldx, const void* dz, int lddz, float* dw, int n, int d, int h, int w, int cin,
+                     int cout, int taps, int dil, void* stream);
+
+/* Backward of b21_norm_apply (mode 0 GroupNorm(8)+ReLU, mode 1 EvoNorm3D-S0) from the pre-norm tensor z and the
+ * forward statistics; dy is the gradient of the layer output.  With se_w1 != NULL the layer output was additionally
+ * multiplied by the MONAI ResidualSELayer gate (b21_se_gate: se_scale, from the channel means se_mean) and dy is the
+ * gradient of that product; the gate's MLP gradients are accumulated into d_w1/d_b1/d_w2/d_b2.  dgamma/dbeta are
+ * accumulated; colsum (optional, fp32 [c]) accumulates sum_v dz (= bias gradient of the producing conv).
+ * workspace: n*c*48 bytes.  dz may alias dy. */
+int b21_norm_bwd(const void* dy, int lddy, const void* z, int ldz, void* dz, int lddz, const double* stats,
+                 const float* gamma, const float* beta, float* dgamma, float* dbeta, float* colsum,
+                 const float* se_scale, const float* se_mean, const float* se_w1, const float* se_b1,
+                 const float* se_w2, const float* se_b2, float* d_w1, float* d_b1, float* d_w2, float* d_b2,
+                 int hidden, void* workspace, long long workspace_bytes, int mode, int n, long long nvox, int c,
+                 float eps, void* stream);
+
+/* Backward of b21_scale_pool modes 1/2: dy = add (optional) + max-routed dpool[:c] (+ dpool[c:2c]/8 for mode 2);
+ * y is the tensor that was pooled. */
+int b21_pool_bwd(const void* y, int ldy, const void* dpool, int ldp, const void* add, int ldadd, void* dy, int lddy,
+                 int mode, int n, int d, int h, int w, int c, void* stream);
+
+/* Adjoints of b21_upsample2x / b21_upsample_f32 (d, h, w are the LOW-resolution dims). */
+int b21_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int n, int d, int h, int w, int c, void* stream);
+int b21_upsample_f32_bwd(const float* dy, float* dx, int planes, int d, int h, int w, int s, void* stream);
+
+/* Backward of b21_head_conv: dx (bf16, += if accumulate) = scale * W^T dl; dws[n][k][c] += sum_v dl x (so that
+ * dW = scale * dws and dscale = sum_k W dws); db[k] += sum_v dl. */
+int b21_head_conv_bwd(const void* x, int ldx, const float* scale, const float* w, const float* dl, void* dx, int lddx,
+                      int accumulate, float* dws, float* db, int n, long long nvox, int c, int k, void* stream);
+
+/* dst += src on ndhwc bf16 (gradient fan-in). */
+int b21_add_inplace(void* dst, int ldd, const void* src, int lds, long long nvox_total, int c, void* stream);
+
+/* monai.losses.DiceLoss(include_background, sigmoid, squared_pred, batch=True, jaccard?) as the reference builds it
+ * (src/definer.py:184-203).  dice_fwd: sums (double [k][3] scratch), loss[0] += weight * mean_k f_k, coef (float
+ * [k][2]) for the backward.  dice_bwd: dlogits = gscale * gout[0] * dloss/dlogits (gout may be NULL = 1). */
+int b21_dice_fwd(const float* logits, const float* target, double* sums, float* loss, float* coef, int n, int k,
+                 long long nvox, int jaccard, float smooth_nr, float smooth_dr, float weight, void* stream);
+int b21_dice_bwd(const float* logits, const float* target, const float* coef, const float* gout, float gscale,
+                 float* dlogits, int n, int k, long long nvox, void* stream);
+
+/* Fused multi-tensor Ranger2020 step (learning/optimizer.py:136-255).  table: int64 [ntensors][6] = {param, grad,
+ * exp_avg, exp_avg_sq, slow_buffer (device pointers, fp32), numel}; chunks: int32 [nchunks][2] = {tensor, offset}
+ * with b21_ranger_chunk() elements per chunk; gscale multiplies every gradient (loss-scale / data-parallel mean). */
+int b21_ranger_chunk(void);
+int b21_ranger_step(const long long* table, const int* chunks, int nchunks, float gscale, float lr, float step_size,
+                    float beta1, float beta2, float eps, float weight_decay, int rectified, int lookahead, float alpha,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

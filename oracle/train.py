@@ -74,9 +74,12 @@ def ranger_step(params: List[torch.Tensor], grads: List[torch.Tensor], states: L
         if n_sma > n_sma_threshold:
             upd = st.exp_avg / (st.exp_avg_sq.sqrt() + eps)
         else:
-            upd = st.exp_avg.clone()
+            upd = st.exp_avg  # aliases the moving average, as `G_grad = exp_avg` does at optimizer.py:231
         if weight_decay != 0:
-            upd = upd + weight_decay * p.detach().float()
+            if n_sma > n_sma_threshold:
+                upd = upd + weight_decay * p.detach().float()
+            else:
+                upd.add_(p.detach().float(), alpha=weight_decay)  # in place: the decay term enters exp_avg
         p.data.add_(upd, alpha=-step_size * lr)
         if st.step % k == 0:
             st.slow.add_(p.data - st.slow, alpha=alpha)
