@@ -39,6 +39,9 @@ WORKLOADS = {
                          "labels; one synthetic 4x240x240x155 volume per step"),
     "v1_sw": dict(version=1, tta=None, mode="constant", sw_batch=4, seed=123,
                   desc="EquiUNet V1 w48, no TTA, 128^3 sliding window (18 windows, batches of 4), labels"),
+    "v2_train": dict(version=2, train=True, seed=93,
+                     desc="EquiUNet-ASPP-Evo w48 training step: forward, Dice over 3 heads, backward, fused Ranger; "
+                          "one synthetic 4x128^3 crop per GPU per step (batch 1/GPU), data-parallel over ranks"),
 }
 
 
@@ -157,9 +160,107 @@ def run_reference(args, wl, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200_train(args, wl, rank, local_rank, world):
+    """BASELINE configs[3]: V2 training step, batch 1 per GPU, data-parallel (NCCL all-reduce overlapped with backward)."""
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import warnings
+    from brats21_b200 import _lib, engine, networks, ops, parallel, synth
+    from brats21_b200.losses import DiceLoss
+    from brats21_b200.optimizer import Ranger2020
+    torch.manual_seed(wl["seed"])
+    feats = [WIDTH * 2 ** i for i in range(4)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = networks.EquiUnetASSPEvo(4, 3, feats, norm_layer="group", act="relu", deep_supervision=True).to(dev).train()
+    model = parallel.DistributedDataParallel(net) if world > 1 else net
+    opt = Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=3e-4, weight_decay=1e-5)
+    if world > 1:
+        model.attach_optimizer(opt)
+    crit = DiceLoss()
+    host_img = synth.volume(seed=2000 + rank, shape=ROI).pin_memory()
+    host_tgt = synth.target(shape=ROI).pin_memory()
+    host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+    img_dev, tgt_dev = host_img.to(dev), host_tgt.to(dev)
+
+    def step_device():
+        return engine.train_step(None, model, crit, opt, img_dev, tgt_dev)
+
+    def step_e2e():
+        img = host_img.to(dev, non_blocking=True)
+        tgt = host_tgt.to(dev, non_blocking=True)
+        loss = engine.train_step(None, model, crit, opt, img, tgt)
+        host_loss.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count
+    ms = timed(step_device, args.steps)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    ops.conv_profile = []
+    step_device()
+    torch.cuda.synchronize()
+    prof, ops.conv_profile = ops.conv_profile, None
+    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+    conv_flops = sum(f for _, _, f, _ in prof)
+    peak_tf, _, peak_kind = measured_peaks()
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    value = world * args.steps / (ms * 1e-3)
+    line = {"metric": "train patches/s (EquiUNet-ASPP-Evo, 128^3, batch 1/GPU)", "value": value, "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl["desc"],
+                       "l2": "activations of one step (>3 GB) far exceed the 126 MB L2",
+                       "parallelism": f"dp{world}: flat-buffer bucketed NCCL all-reduce overlapped with backward"},
+            "clocks": clocks,
+            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "patches/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (host_img.numel() + host_tgt.numel()) * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "conv3d fwd + dgrad + wgrad (tcgen05), all launches of one step",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_kind": f"{peak_kind} bf16 (sustained)", "traffic": None, "launches": len(prof),
+                         "flops_per_launch": conv_flops / max(len(prof), 1), "avg_launch_ms": conv_ms / max(len(prof), 1),
+                         "share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, wl, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    if wl.get("train"):
+        return run_b200_train(args, wl, rank, local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

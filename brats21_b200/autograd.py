@@ -43,7 +43,11 @@ class GradStore:
             self.views[n] = self.flat[off:off + p.numel()].view(p.shape)
             self.offsets[n] = off
             off += p.numel()
-        self.on_ready: Optional[Callable[[int], None]] = None  # called with the flat offset up to which grads are final
+        # data-parallel hooks (brats21_b200.parallel.BucketReducer): start of a backward, "gradients in
+        # flat[0:offset] are final", end of the backward
+        self.on_begin: Optional[Callable[[], None]] = None
+        self.on_ready: Optional[Callable[[int], None]] = None
+        self.on_finish: Optional[Callable[[], None]] = None
 
     def begin(self):
         """Bind .grad views; zero the buffer unless the caller is accumulating into existing gradients."""
@@ -52,6 +56,12 @@ class GradStore:
             self.flat.zero_()
             for p, n in zip(self.params, self.names):
                 p.grad = self.views[n]
+        if self.on_begin is not None:
+            self.on_begin()
+
+    def finish(self):
+        if self.on_finish is not None:
+            self.on_finish()
 
     def ready(self, name: str):
         if self.on_ready is not None:
@@ -336,6 +346,7 @@ class _NetFn(torch.autograd.Function):
         gs.begin()
         with torch.no_grad():
             net._backward_train(ctx.tape, dout, list(ddeeps), gs)
+            gs.finish()
         ctx.tape = None
         return (None, None) + (None,) * len(list(net.parameters()))
 
@@ -348,3 +359,162 @@ def network_forward_train(net, x: torch.Tensor):
     if net.deep_supervision:
         return out, deeps
     return out
+
+
+# ================================================================================================ V1
+GN = ops.GN_RELU
+_V1_HEADS = (("deep_bottom.0", 8), ("deep_bottom2.0", 8), ("deep3.0", 4), ("deep2.0", 2))
+
+
+def v1_grad_order(net) -> List[str]:
+    def cbr(c):
+        return [c + ".bn.weight", c + ".bn.bias", c + ".conv.weight"]
+
+    def ublock(b):
+        return cbr(b + ".ConvBnRelu2") + cbr(b + ".ConvBnRelu1")
+
+    order = ["outconv.weight", "outconv.bias"]
+    order += ublock("decoder1")
+    if net.deep_supervision:
+        order += ["deep2.0.weight", "deep2.0.bias"]
+    order += ublock("decoder2")
+    if net.deep_supervision:
+        order += ["deep3.0.weight", "deep3.0.bias"]
+    order += ublock("decoder3")
+    if net.deep_supervision:
+        order += ["deep_bottom2.0.weight", "deep_bottom2.0.bias"]
+    order += cbr("bottom_2")
+    if net.deep_supervision:
+        order += ["deep_bottom.0.weight", "deep_bottom.0.bias"]
+    order += ublock("bottom") + ublock("encoder4") + ublock("encoder3") + ublock("encoder2") + ublock("encoder1")
+    return order
+
+
+def _v1_forward_train(net, x8: torch.Tensor, want_deep: bool):
+    net._ensure_packed()
+    pk = net._packed
+    if "__train__" not in pk:
+        for name in net._CBR:
+            if name != "encoder1.ConvBnRelu1":
+                pk[name + ".T"] = ops.PackedConv(net.get_submodule(name).conv.weight, None, transpose_flip=True)
+        pk["__train__"] = True
+    n, d, h, w, _ = x8.shape
+    f = net.features
+    ws = net._ws.setdefault(("v1train", n, d, h, w), {})
+    B = lambda name, s, c: net._buf(ws, name, (n, d // s, h // s, w // s, c))  # noqa: E731
+    tape: Dict[str, dict] = {}
+
+    def cbr(name, x, out, s, dil=1):
+        c = out.shape[-1]
+        z = B(name + ".z", s, c)
+        st = net._buf(ws, name + ".st", (ops._lib.STAT_SLOTS, n, 8, 2), torch.float64)
+        ops.conv3d(x, pk[name], out=z, stats=st, dil=dil)
+        ops.norm_apply(z, st, pk[name + ".g"], pk[name + ".b"], GN, out=out)
+        tape[name] = dict(x=x, z=z, st=st, dil=dil)
+        return out
+
+    cat1, cat2, cat3, cat4 = B("cat1", 1, 2 * f[0]), B("cat2", 2, 2 * f[1]), B("cat3", 4, 2 * f[2]), B("cat4", 8, 2 * f[3])
+    p1, p2, p3 = B("p1", 2, f[0]), B("p2", 4, f[1]), B("p3", 8, f[2])
+    down1 = cbr("encoder1.ConvBnRelu2", cbr("encoder1.ConvBnRelu1", x8, B("e1", 1, f[0]), 1), cat1[..., :f[0]], 1)
+    ops.scale_pool(down1, pooled=p1, mode=1)
+    down2 = cbr("encoder2.ConvBnRelu2", cbr("encoder2.ConvBnRelu1", p1, B("e2", 2, f[1]), 2), cat2[..., :f[1]], 2)
+    ops.scale_pool(down2, pooled=p2, mode=1)
+    down3 = cbr("encoder3.ConvBnRelu2", cbr("encoder3.ConvBnRelu1", p2, B("e3", 4, f[2]), 4), cat3[..., :f[2]], 4)
+    ops.scale_pool(down3, pooled=p3, mode=1)
+    down4 = cbr("encoder4.ConvBnRelu2", cbr("encoder4.ConvBnRelu1", p3, B("e4", 8, f[3]), 8), cat4[..., :f[3]], 8)
+    bottom = cbr("bottom.ConvBnRelu2", cbr("bottom.ConvBnRelu1", down4, B("bt", 8, f[3]), 8, dil=2), cat4[..., f[3]:], 8,
+                 dil=2)
+    b2 = cbr("bottom_2", cat4, B("b2", 8, f[2]), 8)
+    ops.upsample2x(b2, cat3[..., f[2]:])
+    u3 = cbr("decoder3.ConvBnRelu2", cbr("decoder3.ConvBnRelu1", cat3, B("d3", 4, f[2]), 4), B("u3", 4, f[1]), 4)
+    ops.upsample2x(u3, cat2[..., f[1]:])
+    u2 = cbr("decoder2.ConvBnRelu2", cbr("decoder2.ConvBnRelu1", cat2, B("d2", 2, f[1]), 2), B("u2", 2, f[0]), 2)
+    ops.upsample2x(u2, cat1[..., f[0]:])
+    u1 = cbr("decoder1.ConvBnRelu2", cbr("decoder1.ConvBnRelu1", cat1, B("d1", 1, f[0]), 1), B("u1", 1, f[0]), 1)
+    out = ops.head_conv(u1, pk["outconv.w"], pk["outconv.bias"])
+    srcs = dict(zip([hname for hname, _ in _V1_HEADS], (bottom, b2, u3, u2)))
+    deeps: List[torch.Tensor] = []
+    if want_deep and net.deep_supervision:
+        for hname, s in _V1_HEADS:
+            deeps.append(ops.upsample_f32(ops.head_conv(srcs[hname], pk[hname + ".w"], pk[hname + ".bias"]), s))
+    tape["__meta__"] = dict(shape=(n, d, h, w), ws=ws, cats=(cat1, cat2, cat3, cat4), srcs=srcs, u1=u1,
+                            want_deep=bool(deeps))
+    return out, deeps, tape
+
+
+def _backward_v1(net, tape, dout, ddeeps, gs: GradStore):
+    pk, G = net._packed, gs.views
+    meta = tape["__meta__"]
+    n, d, h, w = meta["shape"]
+    ws, f = meta["ws"], net.features
+    B = lambda name, s, c: net._buf(ws, "g." + name, (n, d // s, h // s, w // s, c))  # noqa: E731
+    cat1, cat2, cat3, cat4 = meta["cats"]
+    srcs = meta["srcs"]
+    nbw = ops.norm_bwd_workspace(n, 2 * f[3], cat1.device)
+    dl = dict(zip([hname for hname, _ in _V1_HEADS], ddeeps)) if meta["want_deep"] else {}
+
+    def cbr_bwd(name, dy, dx_out):
+        """dy is overwritten with the gradient of the pre-norm conv output."""
+        t = tape[name]
+        ops.norm_bwd(dy, t["z"], dy, t["st"], pk[name + ".g"], pk[name + ".b"], G[name + ".bn.weight"],
+                     G[name + ".bn.bias"], GN, workspace=nbw)
+        ops.conv3d_wgrad(t["x"], dy, G[name + ".conv.weight"], dil=t["dil"])
+        if dx_out is not None:
+            ops.conv3d(dy, pk[name + ".T"], out=dx_out, dil=t["dil"])
+        gs.ready(name + ".conv.weight")
+
+    def head_bwd(pname, x, dlog, dx, accumulate):
+        dws, db = ops.head_conv_bwd(x, pk[pname + ".w"], dlog, dx, accumulate=accumulate)
+        G[pname + ".weight"].view(dws.shape[1], dws.shape[2]).add_(dws.sum(0))
+        G[pname + ".bias"].add_(db)
+        gs.ready(pname + ".bias")
+
+    def deep_bwd(hname, s, dx):
+        g = dl.get(hname)
+        if g is not None:
+            head_bwd(hname, srcs[hname], ops.upsample_f32_bwd(g.float(), s), dx, accumulate=True)
+
+    if dout is None:
+        dout = torch.zeros((n, net.num_classes, d, h, w), dtype=torch.float32, device=cat1.device)
+    g_u1 = B("u1", 1, f[0])
+    head_bwd("outconv", meta["u1"], dout.float(), g_u1, accumulate=False)
+    g_d1, g_cat1 = B("d1", 1, f[0]), B("cat1", 1, 2 * f[0])
+    cbr_bwd("decoder1.ConvBnRelu2", g_u1, g_d1)
+    cbr_bwd("decoder1.ConvBnRelu1", g_d1, g_cat1)
+    g_u2 = B("u2", 2, f[0])
+    ops.upsample2x_bwd(g_cat1[..., f[0]:], g_u2)
+    deep_bwd("deep2.0", 2, g_u2)
+    g_d2, g_cat2 = B("d2", 2, f[1]), B("cat2", 2, 2 * f[1])
+    cbr_bwd("decoder2.ConvBnRelu2", g_u2, g_d2)
+    cbr_bwd("decoder2.ConvBnRelu1", g_d2, g_cat2)
+    g_u3 = B("u3", 4, f[1])
+    ops.upsample2x_bwd(g_cat2[..., f[1]:], g_u3)
+    deep_bwd("deep3.0", 4, g_u3)
+    g_d3, g_cat3 = B("d3", 4, f[2]), B("cat3", 4, 2 * f[2])
+    cbr_bwd("decoder3.ConvBnRelu2", g_u3, g_d3)
+    cbr_bwd("decoder3.ConvBnRelu1", g_d3, g_cat3)
+    g_b2 = B("b2", 8, f[2])
+    ops.upsample2x_bwd(g_cat3[..., f[2]:], g_b2)
+    deep_bwd("deep_bottom2.0", 8, g_b2)
+    g_cat4 = B("cat4", 8, 2 * f[3])
+    cbr_bwd("bottom_2", g_b2, g_cat4)
+    deep_bwd("deep_bottom.0", 8, g_cat4[..., f[3]:])
+    g_bt, g_tmp = B("bt", 8, f[3]), B("tmp4", 8, f[3])
+    cbr_bwd("bottom.ConvBnRelu2", g_cat4[..., f[3]:], g_bt)
+    cbr_bwd("bottom.ConvBnRelu1", g_bt, g_tmp)
+    ops.add_inplace(g_cat4[..., :f[3]], g_tmp)
+    g_e4, g_p3 = B("e4", 8, f[3]), B("p3", 8, f[2])
+    cbr_bwd("encoder4.ConvBnRelu2", g_cat4[..., :f[3]], g_e4)
+    cbr_bwd("encoder4.ConvBnRelu1", g_e4, g_p3)
+    ops.pool_bwd(cat3[..., :f[2]], g_p3, g_cat3[..., :f[2]], 1, add=g_cat3[..., :f[2]])
+    g_e3, g_p2 = B("e3", 4, f[2]), B("p2", 4, f[1])
+    cbr_bwd("encoder3.ConvBnRelu2", g_cat3[..., :f[2]], g_e3)
+    cbr_bwd("encoder3.ConvBnRelu1", g_e3, g_p2)
+    ops.pool_bwd(cat2[..., :f[1]], g_p2, g_cat2[..., :f[1]], 1, add=g_cat2[..., :f[1]])
+    g_e2, g_p1 = B("e2", 2, f[1]), B("p1", 2, f[0])
+    cbr_bwd("encoder2.ConvBnRelu2", g_cat2[..., :f[1]], g_e2)
+    cbr_bwd("encoder2.ConvBnRelu1", g_e2, g_p1)
+    ops.pool_bwd(cat1[..., :f[0]], g_p1, g_cat1[..., :f[0]], 1, add=g_cat1[..., :f[0]])
+    g_e1 = B("e1", 1, f[0])
+    cbr_bwd("encoder1.ConvBnRelu2", g_cat1[..., :f[0]], g_e1)
+    cbr_bwd("encoder1.ConvBnRelu1", g_e1, None)

@@ -53,6 +53,23 @@ def compute_loss(args, criterion, outputs, label=None):
     return outputs, (criterion(outputs, label) if label is not None else None)
 
 
+def train_step(args, model, criterion, optimizer, image, target, scaler=None):
+    """Body of the reference training loop for one batch (learning/engine.py:104-122): zero_grad -> forward ->
+    deep-supervision loss -> backward -> optimizer step.  Returns the loss as a DEVICE tensor: the reference's
+    per-step ``loss.item()`` (engine.py:114) is a host sync the caller can do when it wants the number."""
+    model.zero_grad()
+    outputs = compute_output(args, model, image, is_train=True)
+    _, loss = compute_loss(args, criterion, outputs, target)
+    if scaler is not None:  # torch.cuda.amp.GradScaler as in main_train.py:110 (not needed with bf16)
+        scaler.scale(loss).backward()
+        scaler.step(optimizer)
+        scaler.update()
+    else:
+        loss.backward()
+        optimizer.step()
+    return loss.detach()
+
+
 def apply_tta(args, model, img, tta_transforms: Optional[Compose]) -> List:
     """Drop-in Engine._apply_tta: list (one entry per variant) of de-augmented outputs moved to the CPU."""
     outs = []

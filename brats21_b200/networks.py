@@ -251,6 +251,18 @@ class EquiUnet(_B21Net):
             self._mat(name + ".w", m.weight)
             self._vec(name + ".bias", m.bias)
 
+    def _grad_order(self):
+        from .autograd import v1_grad_order
+        return v1_grad_order(self)
+
+    def _forward_train(self, x8, want_deep):
+        from .autograd import _v1_forward_train
+        return _v1_forward_train(self, x8, want_deep)
+
+    def _backward_train(self, tape, dout, ddeeps, gs):
+        from .autograd import _backward_v1
+        return _backward_v1(self, tape, dout, ddeeps, gs)
+
     def _cbr(self, name, x, out, stats, dil=1):
         p = self._packed
         ops.conv3d(x, p[name], out=out, stats=stats, dil=dil)

@@ -212,7 +212,15 @@ def conv3d_wgrad(x, dz, dw, dil: int = 1):
              stream_ptr())
         dw += tmp[:, :dw.shape[1]]
         return dw
+    prof = conv_profile
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("b21_conv3d_wgrad", ptr(x), _ld(x), ptr(dz), _ld(dz), ptr(dw), n, d, h, w, cin, cout, k ** 3, dil, stream_ptr())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * n * d * h * w * cin * cout * k ** 3, ("wgrad", cin, cout, k ** 3, d)))
     return dw
 
 

@@ -3,6 +3,7 @@ Dice fwd/bwd, norm(+SE) backward, pool / trilinear / head adjoints, conv weight 
 the whole EquiUnetASSPEvo step (loss + every parameter gradient).
 Tolerances: fp32 kernels 1e-4..1e-3 relative; bf16 activations/gradients => a few 2^-8 relative per tensor (stated
 per test)."""
+import contextlib
 import warnings
 
 import pytest
@@ -29,6 +30,36 @@ def _nc(x):
 
 def _rel(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@contextlib.contextmanager
+def _bf16_oracle():
+    """The oracle networks with activations and conv weights rounded to bf16 where the kernels store bf16 (conv and
+    norm outputs, upsampled tensors).  Against the plain fp32 oracle, ReLU masks / max-pool winners of activations
+    within bf16 noise of a tie flip, and the gradient error compounds layer by layer (a property of bf16 training, also
+    of torch autocast); against this emulation the decisions coincide and the comparison isolates kernel errors."""
+    from oracle import nets
+    r = lambda t: t.to(torch.bfloat16).float()  # noqa: E731  (autograd passes the gradient straight through)
+    orig_f, orig_gn, orig_evo, orig_up = nets.F, nets.group_norm_relu, nets.evonorm_s0, nets.up_trilinear
+
+    class _F:
+        def __getattr__(self, k):
+            return getattr(orig_f, k)
+
+        @staticmethod
+        def conv3d(x, w, b=None, **kw):
+            if w.shape[0] == 3:  # class heads run in fp32 on bf16 inputs (head_conv kernel)
+                return orig_f.conv3d(x, w, b, **kw)
+            return r(orig_f.conv3d(r(x), r(w), b, **kw))
+
+    nets.F = _F()
+    nets.group_norm_relu = lambda *a, **k: r(orig_gn(*a, **k))
+    nets.evonorm_s0 = lambda *a, **k: r(orig_evo(*a, **k))
+    nets.up_trilinear = lambda x, scale=2: orig_up(x, scale) if x.shape[1] == 3 else r(orig_up(x, scale))
+    try:
+        yield
+    finally:
+        nets.F, nets.group_norm_relu, nets.evonorm_s0, nets.up_trilinear = orig_f, orig_gn, orig_evo, orig_up
 
 
 @pytest.mark.parametrize("jaccard", [False, True])
@@ -253,10 +284,134 @@ def test_v2_training_step_matches_oracle():
         assert got[name].grad is not None, name
         worst[name] = _rel(got[name].grad, rg)
     bad = {k: v for k, v in worst.items() if v > 0.12}
-    # bf16 activations and gradients through ~40 layers: per-tensor relative L2 stays below 12%, median far lower
+    # vs plain fp32: bf16 activations and gradients through ~40 layers stay below 12% per tensor, median far lower
     assert not bad, f"gradient mismatch: {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"
     med = sorted(worst.values())[len(worst) // 2]
     assert med < 0.05, f"median relative gradient error {med}"
+    with _bf16_oracle():  # vs the bf16-storage emulation of the same math: tight
+        _, emu_grads, _ = _v2_reference_grads(params, x, tgt)
+    bad = {k: _rel(got[k].grad, g) for k, g in emu_grads.items() if _rel(got[k].grad, g) > 0.06}
+    assert not bad, f"gradient mismatch vs bf16-emulating oracle: {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"
     for name, p in got.items():
         if name.endswith(".v"):
             assert p.grad is None  # as in the reference: `v` never enters the efficient EvoNorm path
+
+
+def test_v1_training_step_matches_oracle():
+    """loss and every parameter gradient of one EquiUnet (GroupNorm/ReLU) step (width 16, 32^3) vs torch fp32."""
+    from brats21_b200 import engine, networks
+    from brats21_b200.losses import DiceLoss
+    from oracle import nets, synth
+    from oracle import train as otrain
+    width = 16
+    params = {k: v.to(DEV) for k, v in synth.make_params(1, width, 123).items()}
+    net = networks.EquiUnet(4, 3, [width * 2 ** i for i in range(4)], norm_layer="group", deep_supervision=True).to(DEV)
+    net.load_state_dict(params)
+    net.train()
+    x = synth.volume(seed=5, shape=(32, 32, 32)).to(DEV)
+    tgt = synth.target(shape=(32, 32, 32)).to(DEV)
+    net.zero_grad()
+    outputs = net(x)
+    _, loss = engine.compute_loss(None, DiceLoss(jaccard=True), outputs, tgt)
+    loss.backward()
+    def reference():
+        ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        out, deeps = nets.equiunet_v1_forward(ps, x)
+        ref_loss = otrain.deep_supervision_loss([out] + list(deeps), tgt, True)
+        ref_loss.backward()
+        return ref_loss.detach(), out.detach(), {k: p.grad for k, p in ps.items()}
+
+    got = dict(net.named_parameters())
+    ref_loss, out, grads = reference()
+    assert _rel(outputs[0].detach(), out) < 3e-2
+    assert abs(loss.item() - ref_loss.item()) < 5e-3
+    # vs plain fp32 the ReLU masks of near-zero activations differ (bf16 forward), and the error compounds towards
+    # the first layers (measured: 0.5% at decoder1 ... 30% at encoder1): loose bound, median 10%
+    worst = {name: _rel(got[name].grad, g) for name, g in grads.items()}
+    assert max(worst.values()) < 0.45 and sorted(worst.values())[len(worst) // 2] < 0.10, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    # the yardstick for that drift: torch's own bf16 autocast of the SAME oracle code against its fp32 run
+    ps2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out2, deeps2 = nets.equiunet_v1_forward(ps2, x)
+    otrain.deep_supervision_loss([out2.float()] + [t.float() for t in deeps2], tgt, True).backward()
+    bad = {}
+    for name, g in grads.items():
+        auto = _rel(ps2[name].grad, g)
+        if worst[name] > 1.6 * auto + 0.06:
+            bad[name] = (worst[name], auto)
+    assert not bad, f"gradient error beyond torch-autocast's own: {sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]}"
+
+
+def _ddp_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    from brats21_b200 import engine, networks, parallel
+    from brats21_b200.losses import DiceLoss
+    from brats21_b200.optimizer import Ranger2020
+    from oracle import synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0 (NCCL needs distinct GPUs)
+    try:
+        torch.cuda.set_device(0)
+        width = 16
+        params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net = networks.EquiUnetASSPEvo(4, 3, [width * 2 ** i for i in range(4)], deep_supervision=True).to(DEV)
+        net.load_state_dict(params)
+        net.train()
+        ddp = parallel.DistributedDataParallel(net, bucket_cap_mb=0.25)
+        opt = ddp.attach_optimizer(Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=1e-3))
+        tgt = synth.target(shape=(32, 32, 32)).to(DEV)
+        x = synth.volume(seed=10 + rank, shape=(32, 32, 32)).to(DEV)
+        ddp.zero_grad()
+        _, loss = engine.compute_loss(None, DiceLoss(), ddp(x), tgt)
+        loss.backward()
+        torch.cuda.synchronize()
+        flat_sum = net.grad_store().flat.clone()
+        nb = len(ddp._reducer.bounds)
+        opt.step()
+        torch.cuda.synchronize()
+        out[rank] = (flat_sum.cpu(), torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu(), nb,
+                     ddp._reducer.launched)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradients_are_rank_sums():
+    """world 2 (gloo, both ranks on cuda:0): the bucketed all-reduce leaves every rank with the SUM of the per-rank
+    gradients, the fused optimizer applies the 1/world mean, and the ranks stay bit-identical."""
+    import socket
+    import torch.multiprocessing as mp
+    from brats21_b200 import engine, networks
+    from brats21_b200.losses import DiceLoss
+    from oracle import synth
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+        res = dict(out)
+    (g0, p0, nb, launched), (g1, p1, _, _) = res[0], res[1]
+    assert nb > 3 and launched == nb
+    assert torch.equal(g0, g1) and torch.equal(p0, p1)
+    # single-process reference: sum of the two per-rank gradients
+    width = 16
+    params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = networks.EquiUnetASSPEvo(4, 3, [width * 2 ** i for i in range(4)], deep_supervision=True).to(DEV)
+    net.load_state_dict(params)
+    net.train()
+    tgt = synth.target(shape=(32, 32, 32)).to(DEV)
+    total = None
+    for r in range(2):
+        net.zero_grad()
+        x = synth.volume(seed=10 + r, shape=(32, 32, 32)).to(DEV)
+        _, loss = engine.compute_loss(None, DiceLoss(), net(x), tgt)
+        loss.backward()
+        torch.cuda.synchronize()
+        f = net.grad_store().flat.clone()
+        total = f if total is None else total + f
+    assert _rel(g0.to(DEV), total) < 1e-2  # atomics order differs run to run and bf16 roundings amplify it
