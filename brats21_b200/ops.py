@@ -36,9 +36,10 @@ class PackedConv:
         call("b21_pack_conv_weight", ptr(w32), ptr(self.w), cout, cin, cin_padded, k, int(transpose_flip),
              stream_ptr())
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        lib = _lib.load()
+        self.point_ok = k == 1 and bool(lib.b21_conv_point_supported(cin_padded, rows))
         # plane-marching packing (k = 3, weights resident in shared memory) when the shape allows it
         self.w_march = None
-        lib = _lib.load()
         if k == 3 and lib.b21_conv_march_supported(cin_padded, rows):
             nbytes = lib.b21_conv_march_weight_bytes(cin_padded, rows)
             self.w_march = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
@@ -63,7 +64,10 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    if use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
+    if use_point and pw.taps == 1 and pw.point_ok:
+        call("b21_conv1x1_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
+             n, d * h * w, cin, pw.cout, stream_ptr())
+    elif use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
         call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())
     else:
@@ -80,6 +84,8 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
 conv_profile = None
 # The plane-marching kernel is the default for the shapes it supports; tools flip this to time the tap kernel.
 use_march = True
+# persistent 1x1 kernel (conv_point.cu) for the shapes it supports
+use_point = True
 
 
 # ---------------------------------------------------------------------------------------------- norm / SE / pool

@@ -68,6 +68,14 @@ int b21_pack_conv_weight_march(const float* w, void* packed, int cout, int cin, 
 int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                          double* stats, int n, int d, int h, int w, int cin, int cout, void* stream);
 
+/* Persistent 1x1x1 variant of b21_conv3d_fwd (taps = 1) for the HBM-bound ConvEvo bridges / up-convs
+ * (networks/equiunet2021.py:214-222,262-269): weights resident in shared memory, activation tiles streamed through a
+ * TMA ring, double-buffered TMEM accumulator.  x / y are [n][nvox][ld] bf16; `w_packed` is the k = 1 packing of
+ * b21_pack_conv_weight.  Same bias / stats semantics as b21_conv3d_fwd. */
+int b21_conv_point_supported(int cin, int cout);
+int b21_conv1x1_fwd(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
+                    double* stats, int n, long long nvox, int cin, int cout, void* stream);
+
 /* ------------------------------------------------------------------------------------- normalisation / SE
  * norm_apply: y = GroupNorm(8,C)(x) -> ReLU (mode 0; networks/factory.py:182 + equiunet2020.py:60-61) or
  * EvoNorm3D-S0 (mode 1; networks/equiunet2021.py:48-52,95-105: x*sigmoid(x)/sqrt(var_unbiased+eps)*gamma+beta)

@@ -46,6 +46,46 @@ def test_conv3d_matches_torch(cin, cout, k, dil, shape):
     assert torch.allclose(s[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("cin,cout,shape", [
+    (48, 24, (4, 16, 16, 24)), (96, 48, (2, 5, 7, 9)), (96, 24, (1, 8, 8, 8)), (192, 96, (2, 8, 8, 8)),
+    (192, 48, (1, 3, 5, 7)), (384, 96, (1, 8, 8, 8)), (16, 8, (3, 4, 6, 10)), (128, 32, (1, 9, 9, 9)),
+    (64, 16, (2, 40, 40, 40))])
+def test_conv1x1_persistent_matches_torch_and_tap_kernel(cin, cout, shape):
+    """conv_point.cu (persistent 1x1) against torch fp32 and against the tap kernel, writing into a channel slice of
+    a wider buffer (the concat-free layout) with ragged tile counts and several samples per launch."""
+    from brats21_b200 import _lib, ops
+    assert _lib.load().b21_conv_point_supported(cin, cout)
+    g = torch.Generator(device=DEV).manual_seed(cin * 7 + cout)
+    n, d, h, w = shape
+    x = torch.randn((n, cin, d, h, w), device=DEV, generator=g)
+    wt = torch.randn((cout, cin, 1, 1, 1), device=DEV, generator=g) / cin ** 0.5
+    b = torch.randn((cout,), device=DEV, generator=g)
+    xwide = torch.zeros((n, d, h, w, cin + 8), device=DEV, dtype=torch.bfloat16)
+    xwide[..., 8:] = _cl(x)
+    xb = xwide[..., 8:]
+    pw = ops.PackedConv(wt, b)
+    assert pw.point_ok
+    ywide = torch.full((n, d, h, w, cout + 16), 7.0, device=DEV, dtype=torch.bfloat16)
+    st = ops.new_stats(n, DEV)
+    y = ops.conv3d(xb, pw, out=ywide[..., 8:8 + cout], stats=st)
+    ref = F.conv3d(xb.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), b)
+    assert (_nc(y) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert (ywide[..., :8] == 7).all() and (ywide[..., 8 + cout:] == 7).all()  # neighbours of the slice untouched
+    r = ref.reshape(n, 8, cout // 8, -1).double()
+    s = st.sum(0)
+    assert torch.allclose(s[..., 0], r.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    ops.use_point = False
+    try:
+        st2 = ops.new_stats(n, DEV)
+        y2 = ops.conv3d(xb, pw, stats=st2)
+    finally:
+        ops.use_point = True
+    assert torch.equal(y2, y.contiguous())  # same bf16 inputs, fp32 accumulation over K <= 384: identical roundings
+    y3 = ops.conv3d(xb, ops.PackedConv(wt, None))  # no bias, no stats
+    assert (_nc(y3) - (ref - b.reshape(1, -1, 1, 1, 1))).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
 def test_conv3d_argument_errors():
     from brats21_b200 import ops
     x = torch.zeros((1, 4, 4, 4, 12), device=DEV, dtype=torch.bfloat16)
