@@ -26,6 +26,10 @@ _SIGNATURES = {
     "b21_conv_march_weight_bytes": [_i, _i],
     "b21_pack_conv_weight_march": [_vp, _vp, _i, _i, _i, _vp],
     "b21_conv3d_march_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv_slide_supported": [_i, _i],
+    "b21_conv_slide_weight_bytes": [_i, _i],
+    "b21_pack_conv_weight_slide": [_vp, _vp, _i, _i, _i, _vp],
+    "b21_conv3d_slide_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv_point_supported": [_i, _i],
     "b21_conv1x1_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _vp],
     "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _vp],
@@ -79,6 +83,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = _i
     lib.b21_conv_march_weight_bytes.restype = C.c_longlong
+    lib.b21_conv_slide_weight_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -102,7 +107,7 @@ def stream_ptr():
 
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
-             "b21_conv_march_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
+             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
 launch_count = 0
 
 

@@ -1,0 +1,519 @@
+// conv_slide.cu — "sliding-window" implicit-GEMM conv3d (k = 3, dilation 1, stride 1) for the mid-channel layers
+// (Cin <= 96) whose 27-tap weights do NOT fit in shared memory (conv_march.cu needs them resident).
+//
+// The tap-streaming kernel (conv_tap.cu) re-fetches a 128-voxel activation tile AND a weight tile from L2 for every
+// tap: 1.5 MB of L2 traffic per 128 x 96 x 96 x 27 output tile, which pins the 96 -> 96 layers at 64^3 (31 % of the
+// EquiUNet-ASPP-Evo FLOPs) to the L2 bandwidth (~430 TFLOP/s).  This kernel makes the activations shared-memory
+// resident and amortises every streamed weight tile over three output planes:
+//
+//   * A persistent CTA per SM owns a 16 x 8 (h, w) tile and marches along d in groups of R = 3 output planes, whose
+//     three accumulators (N = NT fp32 columns each) live in a TMEM ring.
+//   * The work is cut into PHASES phi = 3 g + kd.  Phase phi applies the nine (kh, kw) weight tiles of depth tap kd to
+//     the three input halo planes phi-1, phi, phi+1 (relative to the segment), accumulating into the three
+//     output planes of group g.  Because R equals the kernel depth, the window of input planes slides by exactly one
+//     plane per phase: a ring of five 18 x 10 halo planes (three in use, two in flight) is enough, each plane is
+//     fetched from L2 once per segment (TMA, out-of-bounds zero fill = the conv padding), and a (kh, kw) tap is only a
+//     different start address of the UMMA shared-memory descriptor (SWIZZLE_NONE interleaved core matrices, as in
+//     conv_march.cu).
+//   * The weight tiles [Cin x NT] stream through their own TMA ring (cp.async.bulk of the pre-packed UMMA image); each
+//     tile feeds 3 x Cin/16 tcgen05.mma (M = 128, N = NT, K = 16).  L2 traffic per 128 outputs drops from 1.5 MB to
+//     ~0.22 MB (Cin = Cout = 96).
+//   * Warp roles: warp 0 = halo-plane TMA producer, warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer,
+//     warps 3..6 = epilogue (tcgen05.ld -> +bias -> GroupNorm/EvoNorm group statistics -> bf16 NDHWC store), which
+//     drains group g while the MMAs of group g+1 run (TMEM ring of floor(512 / NT) accumulators).
+//
+// Replaces torch.nn.Conv3d(k=3, padding=1) at networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201
+// for 16 <= Cin <= 96, Cout a multiple of the N tile (48 or 96), and is reused for the data gradient with the
+// transposed + mirrored packing.
+#include "ptx.cuh"
+#include "host_common.h"
+#include <stdlib.h>
+
+namespace b21 {
+
+constexpr int kSThreads = 224;
+constexpr int kSTH = 16, kSTW = 8;
+constexpr int kSHH = kSTH + 2, kSHW = kSTW + 2;
+constexpr int kSChunkData = kSHH * kSHW * 16;                  // one 8-channel chunk of a halo plane: 2880 B
+constexpr int kSChunkBytes = (kSChunkData + 127) / 128 * 128;  // 2944 B (TMA destinations are 128 B aligned)
+constexpr int kSMaxPSlots = 8;
+constexpr int kSMaxWStages = 8;
+constexpr int kSMaxRing = 10;
+constexpr int kSSmemBudget = 225 * 1024;
+
+struct ConvSlideParams {
+  __nv_bfloat16* y;
+  const uint8_t* wpk;
+  const float* bias;
+  double* stats;
+  int N, D, H, W, ldy;
+  int kc, ksteps;
+  int tilesH, tilesW, segs, L, ntiles, items;
+  int pslots, wstages, wsub, ks_sub;
+  uint32_t tap_bytes, wstage_bytes;
+};
+
+struct SlideItem {
+  int n, nt, h0, w0, d0, Lc;
+};
+__device__ __forceinline__ SlideItem slide_decode(const ConvSlideParams& p, int item) {
+  SlideItem it;
+  int t = item;
+  const int wt = t % p.tilesW; t /= p.tilesW;
+  const int ht = t % p.tilesH; t /= p.tilesH;
+  it.nt = t % p.ntiles; t /= p.ntiles;
+  const int sg = t % p.segs;
+  it.n = t / p.segs;
+  it.h0 = ht * kSTH;
+  it.w0 = wt * kSTW;
+  it.d0 = sg * p.L;
+  it.Lc = p.D - it.d0 < p.L ? p.D - it.d0 : p.L;
+  return it;
+}
+
+template <int NT, int GS>
+__global__ void __launch_bounds__(kSThreads, 1)
+conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams p) {
+  constexpr uint32_t RING = (512 / NT) < kSMaxRing ? (512 / NT) : kSMaxRing;  // accumulators in TMEM
+  constexpr int NG = NT / GS;                                                 // norm groups covered by one N tile
+  static_assert(NT % 16 == 0 && NT % GS == 0 && NG <= 8 && RING >= 4, "bad tile");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t pfull_bar[kSMaxPSlots];
+  __shared__ __align__(8) uint64_t pempty_bar[kSMaxPSlots];
+  __shared__ __align__(8) uint64_t wfull_bar[kSMaxWStages];
+  __shared__ __align__(8) uint64_t wempty_bar[kSMaxWStages];
+  __shared__ __align__(8) uint64_t accf_bar[kSMaxRing];
+  __shared__ __align__(8) uint64_t acce_bar[kSMaxRing];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_stat[2][16];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const uint32_t w_addr = smem_u32(smem);
+  const uint32_t p_addr = w_addr + uint32_t(p.wstages) * p.wstage_bytes;
+  const uint32_t plane_bytes = uint32_t(p.kc) * kSChunkBytes;
+  const uint32_t pfull0 = smem_u32(&pfull_bar[0]), pempty0 = smem_u32(&pempty_bar[0]);
+  const uint32_t wfull0 = smem_u32(&wfull_bar[0]), wempty0 = smem_u32(&wempty_bar[0]);
+  const uint32_t accf0 = smem_u32(&accf_bar[0]), acce0 = smem_u32(&acce_bar[0]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.pslots; ++s) {
+      mbar_init(&pfull_bar[s], 1);
+      mbar_init(&pempty_bar[s], 1);
+    }
+    for (int s = 0; s < p.wstages; ++s) {
+      mbar_init(&wfull_bar[s], 1);
+      mbar_init(&wempty_bar[s], 1);
+    }
+    for (uint32_t r = 0; r < RING; ++r) {
+      mbar_init(&accf_bar[r], 1);
+      mbar_init(&acce_bar[r], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+  }
+  if (threadIdx.x < 32) s_stat[threadIdx.x >> 4][threadIdx.x & 15] = 0.f;
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ halo-plane producer
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = uint32_t(p.kc) * kSChunkData;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const SlideItem it = slide_decode(p, item);
+        const int G = (it.Lc + 2) / 3;
+        const int NP = 3 * G + 2;
+        for (int j = 0; j < NP; ++j) {
+          mbar_wait_a(pempty0 + 8u * slot, phase ^ 1);
+          const uint32_t fb = pfull0 + 8u * slot;
+          if (j <= it.Lc + 1) {  // planes beyond the segment halo only feed skipped output planes: nothing to load
+            const uint32_t dst = p_addr + uint32_t(slot) * plane_bytes;
+            mbar_expect_tx_a(fb, tx);
+            for (int c = 0; c < p.kc; ++c)
+              tma_load_5d_a(dst + c * kSChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
+          } else {
+            mbar_arrive_a(fb);
+          }
+          if (++slot == p.pslots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ weight producer
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      const uint32_t sub_bytes0 = uint32_t(p.ks_sub) * NT * 32u;
+      const uint32_t sub_bytes1 = uint32_t(p.ksteps - p.ks_sub) * NT * 32u;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const SlideItem it = slide_decode(p, item);
+        const int G = (it.Lc + 2) / 3;
+        const uint8_t* wt = p.wpk + size_t(it.nt) * 27 * p.tap_bytes;
+        for (int g = 0; g < G; ++g) {
+          for (int tap = 0; tap < 27; ++tap) {  // tap = kd * 9 + kh * 3 + kw: phase kd walks taps kd*9 .. kd*9+8
+            for (int sub = 0; sub < p.wsub; ++sub) {
+              mbar_wait_a(wempty0 + 8u * ws, wph ^ 1);
+              const uint32_t nb = sub == 0 ? sub_bytes0 : sub_bytes1;
+              const uint32_t fb = wfull0 + 8u * ws;
+              mbar_expect_tx_a(fb, nb);
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      w_addr + uint32_t(ws) * p.wstage_bytes),
+                  "l"(reinterpret_cast<uint64_t>(wt + size_t(tap) * p.tap_bytes + (sub ? sub_bytes0 : 0u))), "r"(nb),
+                  "r"(fb)
+                  : "memory");
+              if (++ws == p.wstages) {
+                ws = 0;
+                wph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
+      constexpr uint32_t lboB = (NT / 8) * 128, sboB = 128;
+      constexpr uint32_t lboA = kSChunkBytes, sboA = kSHW * 16;
+      const uint64_t dA = umma_smem_desc(0, lboA, sboA, kLayoutNone), dB = umma_smem_desc(0, lboB, sboB, kLayoutNone);
+      const uint32_t idesc = umma_idesc_bf16(128, NT);
+      constexpr uint64_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);
+      int pwait_slot = 0;        // next plane slot to wait for (planes are consumed strictly in ring order)
+      uint32_t pwait_ph = 0;
+      int base_slot = 0;         // ring slot of plane j = 0 of the current item
+      int ws = 0;
+      uint32_t wph = 0;
+      uint32_t acc_slot = 0, acc_par = 0;  // TMEM ring cursor of the first output plane of the current group
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const SlideItem it = slide_decode(p, item);
+        const int G = (it.Lc + 2) / 3;
+        int jwait = 0;
+        for (int g = 0; g < G; ++g) {
+          const int nvalid = it.Lc - 3 * g < 3 ? it.Lc - 3 * g : 3;
+          for (int kd = 0; kd < 3; ++kd) {
+            const int phi = 3 * g + kd;
+            while (jwait <= phi + 2) {
+              mbar_wait_a(pfull0 + 8u * pwait_slot, pwait_ph);
+              if (++pwait_slot == p.pslots) {
+                pwait_slot = 0;
+                pwait_ph ^= 1;
+              }
+              ++jwait;
+            }
+            tc_fence_after();
+            int s0 = base_slot + phi;  // slot of plane j = phi (first plane of the window)
+            s0 %= p.pslots;
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const uint32_t tap_off = uint32_t((t9 / 3) * kSHW + (t9 % 3)) * 16u;
+              for (int sub = 0; sub < p.wsub; ++sub) {
+                mbar_wait_a(wfull0 + 8u * ws, wph);
+                tc_fence_after();
+                const int nks = sub == 0 ? p.ks_sub : p.ksteps - p.ks_sub;
+                const uint32_t a_k0 = sub == 0 ? 0u : uint32_t(p.ks_sub) * 2u * kSChunkBytes;
+                const uint64_t bd0 = dB + uint64_t((w_addr + uint32_t(ws) * p.wstage_bytes) >> 4);
+                const bool first = (kd == 0) && (t9 == 0) && (sub == 0);
+                int sl = s0;
+                uint32_t as = acc_slot, ap = acc_par;
+                for (int r = 0; r < nvalid; ++r) {
+                  if (first) {  // first contribution to this accumulator: the epilogue must have drained the slot
+                    mbar_wait_a(acce0 + 8u * as, ap ^ 1u);
+                    tc_fence_after();
+                  }
+                  uint64_t ad = dA + uint64_t((p_addr + uint32_t(sl) * plane_bytes + tap_off + a_k0) >> 4);
+                  uint64_t bd = bd0;
+                  const uint32_t dcol = tmem_base + as * NT;
+                  for (int ks = 0; ks < nks; ++ks, ad += a_step, bd += b_step)
+                    umma_bf16(dcol, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                  if (++sl == p.pslots) sl = 0;
+                  if (++as == RING) {
+                    as = 0;
+                    ap ^= 1u;
+                  }
+                }
+                umma_commit_a(wempty0 + 8u * ws);
+                if (++ws == p.wstages) {
+                  ws = 0;
+                  wph ^= 1;
+                }
+              }
+            }
+            umma_commit_a(pempty0 + 8u * s0);  // plane j = phi has served its last window
+          }
+          for (int r = 0; r < nvalid; ++r) {  // the group's accumulators are complete
+            umma_commit_a(accf0 + 8u * acc_slot);
+            if (++acc_slot == RING) {
+              acc_slot = 0;
+              acc_par ^= 1u;
+            }
+          }
+        }
+        umma_commit_a(pempty0 + 8u * ((base_slot + 3 * G) % p.pslots));
+        umma_commit_a(pempty0 + 8u * ((base_slot + 3 * G + 1) % p.pslots));
+        base_slot = (base_slot + 3 * G + 2) % p.pslots;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int hh = row >> 3, ww = row & 7;
+    const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
+    uint32_t slot = 0, par = 0;
+    int buf = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const SlideItem it = slide_decode(p, item);
+      const int h = it.h0 + hh, w = it.w0 + ww;
+      const bool valid = (h < p.H) && (w < p.W);
+      const int cbase = it.nt * NT;
+      float gs[NG], gq[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
+      __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy) + cbase;
+      const size_t ystep = size_t(p.H) * p.W * p.ldy;
+      const float* bias = p.bias ? p.bias + cbase : nullptr;
+      for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
+        mbar_wait_a(accf0 + 8u * slot, par);
+        tc_fence_after();
+        float v[NT];
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) tmem_ld16(tlane + slot * NT + uint32_t(c0), v + c0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(acce0 + 8u * slot);  // drained: the MMA warp may start the next group here
+        if (++slot == RING) {
+          slot = 0;
+          par ^= 1u;
+        }
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {
+          const float val = v[c] + (bias ? __ldg(bias + c) : 0.f);
+          v[c] = val;
+          const float sv = valid ? val : 0.f;
+          gs[c / GS] += sv;
+          gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int c0 = 0; c0 < NT; c0 += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
+            o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
+            o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
+            o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
+            *reinterpret_cast<uint4*>(yrow + c0) = o;
+          }
+        }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float a = warp_sum(gs[g]), b = warp_sum(gq[g]);
+          if (lane == 0) {
+            atomicAdd(&s_stat[buf][g * 2], a);
+            atomicAdd(&s_stat[buf][g * 2 + 1], b);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+        if (warp == 3 && lane < 2 * NG) {
+          const float sv = s_stat[buf][lane];
+          s_stat[buf][lane] = 0.f;
+          if (sv != 0.f) {
+            const int slot_s = item % B21_STAT_SLOTS;
+            atomicAdd(p.stats + ((size_t(slot_s) * p.N + it.n) * 8 + it.nt * NG) * 2 + lane, double(sv));
+          }
+        }
+        buf ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ weight repack
+// out = UMMA shared-memory image per (N tile, tap): [ntile][tap = kd*9+kh*3+kw][kc][NT/8][8 n][8 k] bf16.
+__global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
+                                         int cin_o, int rows, int kc, int nt, int transpose_flip) {
+  const int ng = nt / 8;
+  const int ntiles = rows / nt;
+  const size_t total = size_t(ntiles) * 27 * kc * ng * 64;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
+    size_t t = i >> 6;
+    const int g = int(t % ng); t /= ng;
+    const int c = int(t % kc); t /= kc;
+    const int tap = int(t % 27);
+    const int tile = int(t / 27);
+    const int ro = tile * nt + g * 8 + n8;
+    const int ki = c * 8 + k8;
+    float v = 0.f;
+    if (!transpose_flip) {
+      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap];
+    } else {  // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
+      if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + (26 - tap)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int slide_kc(int cin) { return (cin + 15) / 16 * 2; }
+static inline int slide_nt(int cout) { return cout % 96 == 0 ? 96 : (cout % 48 == 0 ? 48 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0))); }
+
+struct SlideCfg {
+  int kc, ksteps, nt, wsub, ks_sub, pslots, wstages;
+  uint32_t tap_bytes, wstage_bytes;
+  size_t smem_bytes;
+};
+static bool slide_config(int cin, int cout, SlideCfg* c) {
+  if (cin < 16 || cin > 96 || cin % 8 || cout % 8) return false;
+  c->nt = slide_nt(cout);
+  if (c->nt == 0) return false;
+  if ((cout / 8) == 0 || c->nt % (cout / 8) != 0) return false;  // whole norm groups per N tile
+  c->kc = slide_kc(cin);
+  c->ksteps = c->kc / 2;
+  c->tap_bytes = uint32_t(c->kc) * c->nt * 16u;
+  c->wsub = c->ksteps >= 4 ? 2 : 1;
+  c->ks_sub = c->wsub == 2 ? (c->ksteps + 1) / 2 : c->ksteps;
+  c->wstage_bytes = (uint32_t(c->ks_sub) * c->nt * 32u + 127u) & ~127u;
+  const size_t plane = size_t(c->kc) * kSChunkBytes;
+  c->pslots = 5;
+  if (size_t(kSSmemBudget) < 128 + 5 * plane + 2 * size_t(c->wstage_bytes)) return false;
+  size_t ws = (size_t(kSSmemBudget) - 128 - 5 * plane) / c->wstage_bytes;
+  c->wstages = int(ws > size_t(kSMaxWStages) ? size_t(kSMaxWStages) : ws);
+  if (c->wstages < (c->wsub == 2 ? 3 : 2)) return false;
+  // spare room -> extra plane slots (deeper halo prefetch)
+  while (c->pslots < kSMaxPSlots &&
+         128 + size_t(c->pslots + 1) * plane + size_t(c->wstages) * c->wstage_bytes <= size_t(kSSmemBudget))
+    ++c->pslots;
+  c->smem_bytes = 128 + size_t(c->pslots) * plane + size_t(c->wstages) * c->wstage_bytes;
+  return true;
+}
+
+template <int NT, int GS>
+static int launch_slide(const CUtensorMap& tm, const ConvSlideParams& p, size_t smem_bytes, int grid,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B21_CUDA(cudaFuncSetAttribute(conv_slide_kernel<NT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSSmemBudget));
+    attr_set = true;
+  }
+  conv_slide_kernel<NT, GS><<<grid, kSThreads, smem_bytes, stream>>>(tm, p);
+  B21_LAUNCH_CHECK("conv_slide_kernel");
+  return B21_OK;
+}
+
+}  // namespace b21
+
+using namespace b21;
+
+extern "C" int b21_conv_slide_supported(int cin, int cout) {
+  SlideCfg c;
+  if (!slide_config(cin, cout, &c)) return 0;
+  const int gs = cout / 8;
+  // instantiated (N tile, channels per norm group) pairs
+  return (c.nt == 96 && (gs == 12 || gs == 24 || gs == 48)) || (c.nt == 48 && gs == 6) || (c.nt == 64 && gs == 8) ||
+                 (c.nt == 32 && gs == 4)
+             ? 1
+             : 0;
+}
+
+extern "C" long long b21_conv_slide_weight_bytes(int cin, int cout) {
+  return (long long)27 * slide_kc(cin) * cout * 16;
+}
+
+extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout, int cin, int transpose_flip,
+                                          void* stream) {
+  B21_CHECK_ARG(w && packed, "pack_conv_weight_slide: null pointer");
+  const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
+  SlideCfg c;
+  B21_CHECK_ARG(slide_config(inner, rows, &c), "pack_conv_weight_slide: (cin %d, cout %d) unsupported", inner, rows);
+  const size_t total = size_t(27) * c.kc * rows * 8;
+  const int threads = 256;
+  const int blocks = int((total + threads - 1) / threads) < 2048 ? int((total + threads - 1) / threads) : 2048;
+  pack_slide_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, c.kc, c.nt, transpose_flip);
+  B21_LAUNCH_CHECK("pack_slide_weight_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
+                                    double* stats, int n, int d, int h, int w, int cin, int cout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B21_CHECK_ARG(x && w_slide && y, "conv3d_slide_fwd: null pointer");
+  B21_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0, "conv3d_slide_fwd: bad shape %d %d %d %d", n, d, h, w);
+  B21_CHECK_ARG(b21_conv_slide_supported(cin, cout), "conv3d_slide_fwd: (cin %d, cout %d) unsupported", cin, cout);
+  B21_CHECK_ARG(ldx >= cin && ldx % 8 == 0 && ldy >= cout && ldy % 8 == 0, "conv3d_slide_fwd: bad ldx %d / ldy %d", ldx, ldy);
+  B21_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(w_slide) & 15) == 0,
+                "conv3d_slide_fwd: pointers must be 16-byte aligned");
+  SlideCfg c;
+  slide_config(cin, cout, &c);
+  ConvSlideParams p;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.wpk = reinterpret_cast<const uint8_t*>(w_slide);
+  p.bias = bias;
+  p.stats = stats;
+  p.N = n; p.D = d; p.H = h; p.W = w; p.ldy = ldy;
+  p.kc = c.kc; p.ksteps = c.ksteps;
+  p.tilesH = (h + kSTH - 1) / kSTH;
+  p.tilesW = (w + kSTW - 1) / kSTW;
+  p.ntiles = cout / c.nt;
+  p.pslots = c.pslots; p.wstages = c.wstages; p.wsub = c.wsub; p.ks_sub = c.ks_sub;
+  p.tap_bytes = c.tap_bytes; p.wstage_bytes = c.wstage_bytes;
+
+  // segment length along d: balance the persistent grid (MMA work is proportional to the planes of an item)
+  const int sms = num_sms();
+  const long long cols = (long long)n * p.tilesH * p.tilesW * p.ntiles;
+  int bestL = d;
+  double best = -1.0;
+  for (int segs = 1; segs <= d; ++segs) {
+    const int L = (d + segs - 1) / segs;
+    if (L < 3 && segs > 1) break;
+    if ((d + L - 1) / L != segs) continue;
+    const long long items = cols * segs;
+    const long long rounds = (items + sms - 1) / sms;
+    const double eff = double(cols) * d / (double(rounds) * sms * (L + 0.5));
+    if (eff > best + 1e-9) {
+      best = eff;
+      bestL = L;
+    }
+  }
+  p.L = bestL;
+  p.segs = (d + p.L - 1) / p.L;
+  p.items = int(cols * p.segs);
+  const int grid = p.items < sms ? p.items : sms;
+
+  CUtensorMap tm;
+  {
+    const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t str[4] = {uint64_t(ldx) * 2, uint64_t(w) * ldx * 2, uint64_t(h) * w * ldx * 2,
+                             uint64_t(d) * h * w * ldx * 2};
+    const uint32_t box[5] = {8, (uint32_t)kSHW, (uint32_t)kSHH, 1, 1};
+    int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
+  if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
+  const int gs = cout / 8;
+  if (c.nt == 96 && gs == 12) return launch_slide<96, 12>(tm, p, c.smem_bytes, grid, stream);
+  if (c.nt == 96 && gs == 24) return launch_slide<96, 24>(tm, p, c.smem_bytes, grid, stream);
+  if (c.nt == 96 && gs == 48) return launch_slide<96, 48>(tm, p, c.smem_bytes, grid, stream);
+  if (c.nt == 48 && gs == 6) return launch_slide<48, 6>(tm, p, c.smem_bytes, grid, stream);
+  if (c.nt == 64 && gs == 8) return launch_slide<64, 8>(tm, p, c.smem_bytes, grid, stream);
+  return launch_slide<32, 4>(tm, p, c.smem_bytes, grid, stream);
+}

@@ -45,6 +45,13 @@ class PackedConv:
             self.w_march = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
             call("b21_pack_conv_weight_march", ptr(w32), ptr(self.w_march), cout, cin, int(transpose_flip),
                  stream_ptr())
+        # sliding-window packing (k = 3, 16 <= cin <= 96, weights streamed per tap)
+        self.w_slide = None
+        if k == 3 and self.w_march is None and lib.b21_conv_slide_supported(cin_padded, rows):
+            nbytes = lib.b21_conv_slide_weight_bytes(cin_padded, rows)
+            self.w_slide = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
+            call("b21_pack_conv_weight_slide", ptr(w32), ptr(self.w_slide), cout, cin, int(transpose_flip),
+                 stream_ptr())
 
 
 def new_stats(n: int, device) -> torch.Tensor:
@@ -70,6 +77,9 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
     elif use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
         call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())
+    elif use_slide and dil == 1 and pw.w_slide is not None and h >= 8 and w >= 8:
+        call("b21_conv3d_slide_fwd", ptr(x), _ld(x), ptr(pw.w_slide), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
+             n, d, h, w, cin, pw.cout, stream_ptr())
     else:
         call("b21_conv3d_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
@@ -84,6 +94,8 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
 conv_profile = None
 # The plane-marching kernel is the default for the shapes it supports; tools flip this to time the tap kernel.
 use_march = True
+# sliding-window kernel (conv_slide.cu) for the k = 3 shapes whose weights do not fit the march kernel
+use_slide = True
 # persistent 1x1 kernel (conv_point.cu) for the shapes it supports
 use_point = True
 

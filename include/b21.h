@@ -68,6 +68,18 @@ int b21_pack_conv_weight_march(const float* w, void* packed, int cout, int cin, 
 int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                          double* stats, int n, int d, int h, int w, int cin, int cout, void* stream);
 
+/* Sliding-window variant of b21_conv3d_fwd for k = 3, dilation 1 layers with 16 <= cin <= 96 whose weights do not fit
+ * in shared memory (b21_conv_slide_supported): 18 x 10 halo planes are shared-memory resident (each read once per
+ * d-segment), the 27 weight tiles stream through a TMA ring and each feeds three output planes held in a TMEM ring.
+ * Same semantics (bias, stats, channel-slice ld) as b21_conv3d_fwd with taps = 27, dil = 1.  The weight is packed by
+ * b21_pack_conv_weight_slide into b21_conv_slide_weight_bytes(cin, cout) bytes:
+ * bf16 [cout/NT][kd*9+kh*3+kw][ceil16(cin)/8][NT/8][8 n][8 k]; `transpose_flip` as above. */
+int b21_conv_slide_supported(int cin, int cout);
+long long b21_conv_slide_weight_bytes(int cin, int cout);
+int b21_pack_conv_weight_slide(const float* w, void* packed, int cout, int cin, int transpose_flip, void* stream);
+int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
+                         double* stats, int n, int d, int h, int w, int cin, int cout, void* stream);
+
 /* Persistent 1x1x1 variant of b21_conv3d_fwd (taps = 1) for the HBM-bound ConvEvo bridges / up-convs
  * (networks/equiunet2021.py:214-222,262-269): weights resident in shared memory, activation tiles streamed through a
  * TMA ring, double-buffered TMEM accumulator.  x / y are [n][nvox][ld] bf16; `w_packed` is the k = 1 packing of

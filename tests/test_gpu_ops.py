@@ -86,6 +86,45 @@ def test_conv1x1_persistent_matches_torch_and_tap_kernel(cin, cout, shape):
     assert (_nc(y3) - (ref - b.reshape(1, -1, 1, 1, 1))).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("cin,cout,shape", [
+    (96, 96, (1, 8, 16, 8)), (96, 96, (2, 7, 20, 12)), (96, 96, (1, 32, 32, 32)), (48, 96, (1, 9, 16, 16)),
+    (96, 48, (1, 10, 8, 24)), (64, 64, (2, 5, 9, 11)), (96, 192, (1, 4, 16, 8)), (32, 96, (1, 3, 8, 8)),
+    (80, 96, (1, 13, 17, 9))])
+def test_conv3d_slide_matches_torch(cin, cout, shape):
+    """conv_slide.cu (smem-resident halo planes, streamed weight taps, 3 output planes per tap) against torch fp32,
+    reading/writing channel slices of wider buffers, with ragged tiles, several d-segments and samples."""
+    from brats21_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin * 31 + cout)
+    n, d, h, w = shape
+    x = torch.randn((n, cin, d, h, w), device=DEV, generator=g)
+    wt = torch.randn((cout, cin, 3, 3, 3), device=DEV, generator=g) / (cin * 27) ** 0.5
+    b = torch.randn((cout,), device=DEV, generator=g)
+    xwide = torch.zeros((n, d, h, w, cin + 16), device=DEV, dtype=torch.bfloat16)
+    xwide[..., 8:8 + cin] = _cl(x)
+    xwide[..., :8] = 3.0
+    xwide[..., 8 + cin:] = -5.0  # neighbours of the input slice must not leak in
+    xb = xwide[..., 8:8 + cin]
+    pw = ops.PackedConv(wt, b)
+    assert pw.w_slide is not None and pw.w_march is None
+    ywide = torch.full((n, d, h, w, cout + 16), 7.0, device=DEV, dtype=torch.bfloat16)
+    st = ops.new_stats(n, DEV)
+    y = ops.conv3d(xb, pw, out=ywide[..., 8:8 + cout], stats=st)
+    ref = F.conv3d(xb.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), b, padding=1)
+    assert (_nc(y) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert (ywide[..., :8] == 7).all() and (ywide[..., 8 + cout:] == 7).all()
+    r = ref.reshape(n, 8, cout // 8, -1).double()
+    s = st.sum(0)
+    assert torch.allclose(s[..., 0], r.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    # data-gradient packing (transposed + mirrored) == conv_transpose3d
+    pt = ops.PackedConv(wt, None, transpose_flip=True)
+    if pt.w_slide is not None:
+        dy = _cl(torch.randn((n, cout, d, h, w), device=DEV, generator=g))
+        dx = ops.conv3d(dy, pt)
+        ref_dx = F.conv_transpose3d(dy.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), padding=1)
+        assert (_nc(dx) - ref_dx).abs().max().item() <= 2 ** -7 * ref_dx.abs().max().item()
+
+
 def test_conv3d_argument_errors():
     from brats21_b200 import ops
     x = torch.zeros((1, 4, 4, 4, 12), device=DEV, dtype=torch.bfloat16)
