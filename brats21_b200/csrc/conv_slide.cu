@@ -51,6 +51,7 @@ struct ConvSlideParams {
   int tilesH, tilesW, segs, L, ntiles, items;
   int pslots, wstages, wsub, ks_sub;
   uint32_t tap_bytes, wstage_bytes;
+  int variant;  // debug (B21_SLIDE_VARIANT): bit0 no plane loads, bit1 no weight loads, bit2 no epilogue math/stores, bit3 one MMA per stage
 };
 
 struct SlideItem {
@@ -71,7 +72,7 @@ __device__ __forceinline__ SlideItem slide_decode(const ConvSlideParams& p, int 
   return it;
 }
 
-template <int NT, int GS>
+template <int NT, int GS, int KS0, int KS1>  // N tile, channels per norm group, k-steps of the two weight sub-stages
 __global__ void __launch_bounds__(kSThreads, 1)
 conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams p) {
   constexpr uint32_t RING = (512 / NT) < kSMaxRing ? (512 / NT) : kSMaxRing;  // accumulators in TMEM
@@ -135,7 +136,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
         for (int j = 0; j < NP; ++j) {
           mbar_wait_a(pempty0 + 8u * slot, phase ^ 1);
           const uint32_t fb = pfull0 + 8u * slot;
-          if (j <= it.Lc + 1) {  // planes beyond the segment halo only feed skipped output planes: nothing to load
+          if (j <= it.Lc + 1 && !(p.variant & 1)) {  // planes beyond the segment halo only feed skipped output planes: nothing to load
             const uint32_t dst = p_addr + uint32_t(slot) * plane_bytes;
             mbar_expect_tx_a(fb, tx);
             for (int c = 0; c < p.kc; ++c)
@@ -155,18 +156,22 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
     if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
-      const uint32_t sub_bytes0 = uint32_t(p.ks_sub) * NT * 32u;
-      const uint32_t sub_bytes1 = uint32_t(p.ksteps - p.ks_sub) * NT * 32u;
+      constexpr uint32_t sub_bytes0 = uint32_t(KS0) * NT * 32u;
+      constexpr uint32_t sub_bytes1 = uint32_t(KS1) * NT * 32u;
+      constexpr int kWsub = KS1 > 0 ? 2 : 1;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const SlideItem it = slide_decode(p, item);
         const int G = (it.Lc + 2) / 3;
         const uint8_t* wt = p.wpk + size_t(it.nt) * 27 * p.tap_bytes;
         for (int g = 0; g < G; ++g) {
           for (int tap = 0; tap < 27; ++tap) {  // tap = kd * 9 + kh * 3 + kw: phase kd walks taps kd*9 .. kd*9+8
-            for (int sub = 0; sub < p.wsub; ++sub) {
+            for (int sub = 0; sub < kWsub; ++sub) {
               mbar_wait_a(wempty0 + 8u * ws, wph ^ 1);
               const uint32_t nb = sub == 0 ? sub_bytes0 : sub_bytes1;
               const uint32_t fb = wfull0 + 8u * ws;
+              if (p.variant & 2) {
+                mbar_arrive_a(fb);
+              } else {
               mbar_expect_tx_a(fb, nb);
               asm volatile(
                   "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -174,6 +179,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
                   "l"(reinterpret_cast<uint64_t>(wt + size_t(tap) * p.tap_bytes + (sub ? sub_bytes0 : 0u))), "r"(nb),
                   "r"(fb)
                   : "memory");
+              }
               if (++ws == p.wstages) {
                 ws = 0;
                 wph ^= 1;
@@ -185,15 +191,23 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    // The loop is written for a low instruction count per tcgen05.mma: k-steps per weight stage are compile-time
+    // (immediate descriptor offsets), the three A descriptors of a phase and the accumulator columns are computed once
+    // per phase, ring cursors are running counters.
     if (elect_one()) {
       constexpr uint32_t lboB = (NT / 8) * 128, sboB = 128;
       constexpr uint32_t lboA = kSChunkBytes, sboA = kSHW * 16;
       const uint64_t dA = umma_smem_desc(0, lboA, sboA, kLayoutNone), dB = umma_smem_desc(0, lboB, sboB, kLayoutNone);
+      const uint32_t a_hi = uint32_t(dA >> 32), b_hi = uint32_t(dB >> 32);
+      const uint32_t a_lo_base = uint32_t(dA) + (p_addr >> 4);  // address field: bits [0,14), smem < 256 KB: no carry
+      const uint32_t b_lo_base = uint32_t(dB) + (w_addr >> 4);
+      const uint32_t plane16 = plane_bytes >> 4, wstage16 = p.wstage_bytes >> 4;
       const uint32_t idesc = umma_idesc_bf16(128, NT);
-      constexpr uint64_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);
+      constexpr uint32_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);  // one k-step (16 channels), 16 B units
+      const int pslots = p.pslots, wstages = p.wstages;
       int pwait_slot = 0;        // next plane slot to wait for (planes are consumed strictly in ring order)
       uint32_t pwait_ph = 0;
-      int base_slot = 0;         // ring slot of plane j = 0 of the current item
+      int win_slot = 0;          // ring slot of plane j = phi (first plane of the current window)
       int ws = 0;
       uint32_t wph = 0;
       uint32_t acc_slot = 0, acc_par = 0;  // TMEM ring cursor of the first output plane of the current group
@@ -203,54 +217,86 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
         int jwait = 0;
         for (int g = 0; g < G; ++g) {
           const int nvalid = it.Lc - 3 * g < 3 ? it.Lc - 3 * g : 3;
+          uint32_t as1 = acc_slot + 1, ap1 = acc_par;
+          if (as1 == RING) { as1 = 0; ap1 ^= 1u; }
+          uint32_t as2 = as1 + 1, ap2 = ap1;
+          if (as2 == RING) { as2 = 0; ap2 ^= 1u; }
+          const uint32_t dcol0 = tmem_base + acc_slot * NT, dcol1 = tmem_base + as1 * NT, dcol2 = tmem_base + as2 * NT;
           for (int kd = 0; kd < 3; ++kd) {
             const int phi = 3 * g + kd;
             while (jwait <= phi + 2) {
               mbar_wait_a(pfull0 + 8u * pwait_slot, pwait_ph);
-              if (++pwait_slot == p.pslots) {
+              if (++pwait_slot == pslots) {
                 pwait_slot = 0;
                 pwait_ph ^= 1;
               }
               ++jwait;
             }
             tc_fence_after();
-            int s0 = base_slot + phi;  // slot of plane j = phi (first plane of the window)
-            s0 %= p.pslots;
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t tap_off = uint32_t((t9 / 3) * kSHW + (t9 % 3)) * 16u;
-              for (int sub = 0; sub < p.wsub; ++sub) {
-                mbar_wait_a(wfull0 + 8u * ws, wph);
-                tc_fence_after();
-                const int nks = sub == 0 ? p.ks_sub : p.ksteps - p.ks_sub;
-                const uint32_t a_k0 = sub == 0 ? 0u : uint32_t(p.ks_sub) * 2u * kSChunkBytes;
-                const uint64_t bd0 = dB + uint64_t((w_addr + uint32_t(ws) * p.wstage_bytes) >> 4);
-                const bool first = (kd == 0) && (t9 == 0) && (sub == 0);
-                int sl = s0;
-                uint32_t as = acc_slot, ap = acc_par;
-                for (int r = 0; r < nvalid; ++r) {
-                  if (first) {  // first contribution to this accumulator: the epilogue must have drained the slot
-                    mbar_wait_a(acce0 + 8u * as, ap ^ 1u);
-                    tc_fence_after();
+            int s1 = win_slot + 1;
+            if (s1 == pslots) s1 = 0;
+            int s2 = s1 + 1;
+            if (s2 == pslots) s2 = 0;
+            const uint32_t a0 = a_lo_base + uint32_t(win_slot) * plane16, a1 = a_lo_base + uint32_t(s1) * plane16,
+                           a2 = a_lo_base + uint32_t(s2) * plane16;
+#pragma unroll 1
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t tap16 = uint32_t(kh * kSHW + kw);
+                const uint32_t fresh = (kd | kh | kw) == 0 ? 1u : 0u;  // first contribution to the group's accumulators
+                {
+                  mbar_wait_a(wfull0 + 8u * ws, wph);
+                  tc_fence_after();
+                  const uint32_t b_lo = b_lo_base + uint32_t(ws) * wstage16;
+#pragma unroll
+                  for (int r = 0; r < 3; ++r) {
+                    if (r < nvalid) {
+                      const uint32_t as = r == 0 ? acc_slot : (r == 1 ? as1 : as2);
+                      const uint32_t ap = r == 0 ? acc_par : (r == 1 ? ap1 : ap2);
+                      const uint32_t dcol = r == 0 ? dcol0 : (r == 1 ? dcol1 : dcol2);
+                      const uint32_t al = (r == 0 ? a0 : (r == 1 ? a1 : a2)) + tap16;
+                      if (fresh) {  // the epilogue must have drained this TMEM slot
+                        mbar_wait_a(acce0 + 8u * as, ap ^ 1u);
+                        tc_fence_after();
+                      }
+#pragma unroll
+                      for (int ks = 0; ks < KS0; ++ks)
+                        umma_bf16(dcol, (uint64_t(a_hi) << 32) | (al + ks * a_step),
+                                  (uint64_t(b_hi) << 32) | (b_lo + ks * b_step), idesc, (ks == 0 ? fresh ^ 1u : 1u));
+                    }
                   }
-                  uint64_t ad = dA + uint64_t((p_addr + uint32_t(sl) * plane_bytes + tap_off + a_k0) >> 4);
-                  uint64_t bd = bd0;
-                  const uint32_t dcol = tmem_base + as * NT;
-                  for (int ks = 0; ks < nks; ++ks, ad += a_step, bd += b_step)
-                    umma_bf16(dcol, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-                  if (++sl == p.pslots) sl = 0;
-                  if (++as == RING) {
-                    as = 0;
-                    ap ^= 1u;
+                  umma_commit_a(wempty0 + 8u * ws);
+                  if (++ws == wstages) {
+                    ws = 0;
+                    wph ^= 1;
                   }
                 }
-                umma_commit_a(wempty0 + 8u * ws);
-                if (++ws == p.wstages) {
-                  ws = 0;
-                  wph ^= 1;
+                if (KS1 > 0) {
+                  mbar_wait_a(wfull0 + 8u * ws, wph);
+                  tc_fence_after();
+                  const uint32_t b_lo = b_lo_base + uint32_t(ws) * wstage16;
+#pragma unroll
+                  for (int r = 0; r < 3; ++r) {
+                    if (r < nvalid) {
+                      const uint32_t dcol = r == 0 ? dcol0 : (r == 1 ? dcol1 : dcol2);
+                      const uint32_t al = (r == 0 ? a0 : (r == 1 ? a1 : a2)) + tap16 + KS0 * a_step;
+#pragma unroll
+                      for (int ks = 0; ks < KS1; ++ks)
+                        umma_bf16(dcol, (uint64_t(a_hi) << 32) | (al + ks * a_step),
+                                  (uint64_t(b_hi) << 32) | (b_lo + ks * b_step), idesc, 1u);
+                    }
+                  }
+                  umma_commit_a(wempty0 + 8u * ws);
+                  if (++ws == wstages) {
+                    ws = 0;
+                    wph ^= 1;
+                  }
                 }
               }
             }
-            umma_commit_a(pempty0 + 8u * s0);  // plane j = phi has served its last window
+            umma_commit_a(pempty0 + 8u * win_slot);  // plane j = phi has served its last window
+            win_slot = s1;
           }
           for (int r = 0; r < nvalid; ++r) {  // the group's accumulators are complete
             umma_commit_a(accf0 + 8u * acc_slot);
@@ -260,9 +306,11 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
             }
           }
         }
-        umma_commit_a(pempty0 + 8u * ((base_slot + 3 * G) % p.pslots));
-        umma_commit_a(pempty0 + 8u * ((base_slot + 3 * G + 1) % p.pslots));
-        base_slot = (base_slot + 3 * G + 2) % p.pslots;
+        // the two trailing halo planes (j = 3G, 3G+1)
+        umma_commit_a(pempty0 + 8u * win_slot);
+        if (++win_slot == pslots) win_slot = 0;
+        umma_commit_a(pempty0 + 8u * win_slot);
+        if (++win_slot == pslots) win_slot = 0;
       }
     }
   } else {
@@ -298,6 +346,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           slot = 0;
           par ^= 1u;
         }
+        if (p.variant & 4) continue;
 #pragma unroll
         for (int c = 0; c < NT; ++c) {
           const float val = v[c] + (bias ? __ldg(bias + c) : 0.f);
@@ -404,18 +453,32 @@ static bool slide_config(int cin, int cout, SlideCfg* c) {
   return true;
 }
 
-template <int NT, int GS>
+template <int NT, int GS, int KS0, int KS1>
 static int launch_slide(const CUtensorMap& tm, const ConvSlideParams& p, size_t smem_bytes, int grid,
                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    B21_CUDA(cudaFuncSetAttribute(conv_slide_kernel<NT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B21_CUDA(cudaFuncSetAttribute(conv_slide_kernel<NT, GS, KS0, KS1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kSSmemBudget));
     attr_set = true;
   }
-  conv_slide_kernel<NT, GS><<<grid, kSThreads, smem_bytes, stream>>>(tm, p);
+  conv_slide_kernel<NT, GS, KS0, KS1><<<grid, kSThreads, smem_bytes, stream>>>(tm, p);
   B21_LAUNCH_CHECK("conv_slide_kernel");
   return B21_OK;
+}
+
+// Instantiated shapes: (N tile, channels per norm group, k-steps of weight sub-stage 0 / 1).
+//   96 -> 96   EquiUNet-ASPP-Evo encoder2/decoder2 (+ data gradients), EquiUNet encoder2.2
+//   48 -> 96   EquiUNet encoder2.1;  96 -> 48  EquiUNet decoder1.1 / decoder2.2;  96 -> 192  EquiUNet encoder3.1
+//   64 -> 64   level 3 of the width-16 networks the parity tests run
+#define B21_SLIDE_SHAPES(X) X(96, 12, 3, 3) X(96, 12, 3, 0) X(48, 6, 3, 3) X(96, 24, 3, 3) X(64, 8, 2, 2)
+
+static bool slide_instantiated(const SlideCfg& c, int cout) {
+  const int gs = cout / 8, ks1 = c.ksteps - c.ks_sub;
+#define X(nt_, g_, k0, k1) if (c.nt == nt_ && gs == g_ && c.ks_sub == k0 && ks1 == k1) return true;
+  B21_SLIDE_SHAPES(X)
+#undef X
+  return false;
 }
 
 }  // namespace b21
@@ -425,12 +488,7 @@ using namespace b21;
 extern "C" int b21_conv_slide_supported(int cin, int cout) {
   SlideCfg c;
   if (!slide_config(cin, cout, &c)) return 0;
-  const int gs = cout / 8;
-  // instantiated (N tile, channels per norm group) pairs
-  return (c.nt == 96 && (gs == 12 || gs == 24 || gs == 48)) || (c.nt == 48 && gs == 6) || (c.nt == 64 && gs == 8) ||
-                 (c.nt == 32 && gs == 4)
-             ? 1
-             : 0;
+  return slide_instantiated(c, cout) ? 1 : 0;
 }
 
 extern "C" long long b21_conv_slide_weight_bytes(int cin, int cout) {
@@ -476,6 +534,12 @@ extern "C" int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide,
   p.ntiles = cout / c.nt;
   p.pslots = c.pslots; p.wstages = c.wstages; p.wsub = c.wsub; p.ks_sub = c.ks_sub;
   p.tap_bytes = c.tap_bytes; p.wstage_bytes = c.wstage_bytes;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("B21_SLIDE_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  p.variant = variant;
 
   // segment length along d: balance the persistent grid (MMA work is proportional to the planes of an item)
   const int sms = num_sms();
@@ -509,11 +573,12 @@ extern "C" int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide,
     if (r) return r;
   }
   if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
-  const int gs = cout / 8;
-  if (c.nt == 96 && gs == 12) return launch_slide<96, 12>(tm, p, c.smem_bytes, grid, stream);
-  if (c.nt == 96 && gs == 24) return launch_slide<96, 24>(tm, p, c.smem_bytes, grid, stream);
-  if (c.nt == 96 && gs == 48) return launch_slide<96, 48>(tm, p, c.smem_bytes, grid, stream);
-  if (c.nt == 48 && gs == 6) return launch_slide<48, 6>(tm, p, c.smem_bytes, grid, stream);
-  if (c.nt == 64 && gs == 8) return launch_slide<64, 8>(tm, p, c.smem_bytes, grid, stream);
-  return launch_slide<32, 4>(tm, p, c.smem_bytes, grid, stream);
+  const int gs = cout / 8, ks1 = c.ksteps - c.ks_sub;
+#define X(nt_, g_, k0, k1) \
+  if (c.nt == nt_ && gs == g_ && c.ks_sub == k0 && ks1 == k1) \
+    return launch_slide<nt_, g_, k0, k1>(tm, p, c.smem_bytes, grid, stream);
+  B21_SLIDE_SHAPES(X)
+#undef X
+  set_error("conv3d_slide_fwd: shape not instantiated");
+  return B21_ERR_UNSUPPORTED;
 }
