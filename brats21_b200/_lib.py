@@ -37,7 +37,17 @@ _SIGNATURES = {
     "b21_scale_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_upsample2x": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_upsample_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b21_head_conv": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "b21_head_conv": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "b21_evo_se_affine": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _f, _vp],
+    "b21_border_weight_sums": [_vp, _vp, _i, _i, _i, _vp],
+    "b21_bias_table": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "b21_pack_conv_weight_fold": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "b21_pack_conv_weight_march_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp],
+    "b21_pack_conv_weight_slide_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp],
+    "b21_conv3d_march_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv3d_slide_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv1x1_fwd_fold": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp],
+    "b21_affine_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_pack_windows": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b21_blend_accumulate": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "b21_tta_accumulate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp],

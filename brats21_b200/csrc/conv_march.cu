@@ -22,6 +22,7 @@
 // Replaces torch.nn.Conv3d(k=3, padding=1) at networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201
 // for the layers whose weights fit in shared memory (54 * ceil16(Cin) * Cout bytes); other shapes use conv_tap.cu.
 #include "ptx.cuh"
+#include "fold.cuh"
 #include "host_common.h"
 #include <stdlib.h>
 
@@ -46,6 +47,7 @@ struct ConvMarchParams {
   int tilesH, tilesW, segs, L, items;
   int stages, ring;
   uint32_t wbytes;
+  FoldExtras ex;
   int variant;  // debug (B21_MARCH_VARIANT): bit2 no TMA loads, bit3 no stores, bit4 three taps only, bit5 no epilogue math/stores, bit6 no TMEM ld/st
 };
 
@@ -119,16 +121,28 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: weights once, then planes
     if (elect_one()) {
-      mbar_expect_tx(&w_bar, p.wbytes);
-      for (uint32_t off = 0; off < p.wbytes; off += 16384u) {
-        const uint32_t nb = p.wbytes - off < 16384u ? p.wbytes - off : 16384u;
-        bulk_load_1d(smem + off, p.wpk + off, nb, &w_bar);
-      }
       int stage = 0;
       uint32_t phase = 0;
+      int w_n = -1;  // sample whose weights are resident (per-sample weights: folded EvoNorm affine)
       const uint32_t tx = uint32_t(p.kc) * kMChunkData;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const MarchItem it = decode_item(p, item);
+        if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
+          if (w_n >= 0) {
+            // every plane stage released <=> every MMA that read the old weights has completed
+            for (int k = 0; k < p.stages; ++k) {
+              const int s2 = stage + k < p.stages ? stage + k : stage + k - p.stages;
+              mbar_wait_a(empty0 + 8u * s2, (stage + k < p.stages ? phase : phase ^ 1) ^ 1);
+            }
+          }
+          w_n = it.n;
+          const uint8_t* wsrc = p.wpk + size_t(p.ex.wstride) * it.n;
+          mbar_expect_tx(&w_bar, p.wbytes);
+          for (uint32_t off = 0; off < p.wbytes; off += 16384u) {
+            const uint32_t nb = p.wbytes - off < 16384u ? p.wbytes - off : 16384u;
+            bulk_load_1d(smem + off, wsrc + off, nb, &w_bar);
+          }
+        }
         for (int i = 0; i <= it.Lc + 1; ++i) {
           const int dz = it.d0 - 1 + i;
           if (dz < 0 || dz >= p.D) continue;
@@ -161,13 +175,19 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       const uint64_t bd0 = dB + uint64_t(w_addr >> 4);
       const int ksteps = p.kc >> 1;
       const int nkh = (p.variant & 16) ? 1 : 3;
-      mbar_wait(&w_bar, 0);
-      tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0;
+      int w_n = -1;
+      uint32_t w_par = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const MarchItem it = decode_item(p, item);
+        if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
+          w_n = it.n;
+          mbar_wait(&w_bar, w_par);
+          w_par ^= 1u;
+          tc_fence_after();
+        }
         uint32_t r_lo = r_base;
         for (int i = 0; i <= it.Lc + 1; ++i) {
           // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j; the lowest valid
@@ -259,6 +279,13 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       float gs[8], gq[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+      constexpr int NCS = (COUT + 31) / 32;
+      float csum[NCS];  // lane l: running sum of the stored outputs of channels l, 32 + l, ...
+#pragma unroll
+      for (int b = 0; b < NCS; ++b) csum[b] = 0.f;
+      const float* trow = p.ex.table
+                              ? p.ex.table + (size_t(it.n) * 27 + border_class(h, p.H) * 3 + border_class(w, p.W)) * COUT
+                              : nullptr;
       __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy);
       const size_t ystep = size_t(p.H) * p.W * p.ldy;
       for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
@@ -282,25 +309,61 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
         if (lane == 0) mbar_arrive_a(acce0 + 8u * r);  // slot drained + zeroed: the MMA warp may reuse it
         r = r + 1 == RING ? 0 : r + 1;
         if (p.variant & 32) continue;  // debug: handshake only
+        if (trow && valid) {  // folded input affine: the bias depends on the border class of the output voxel
+          const float4* tb = reinterpret_cast<const float4*>(trow + size_t(border_class(it.d0 + so, p.D)) * 9 * COUT);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 t4 = __ldg(tb + c4);
+            v[c4 * 4 + 0] += t4.x; v[c4 * 4 + 1] += t4.y; v[c4 * 4 + 2] += t4.z; v[c4 * 4 + 3] += t4.w;
+          }
+        } else if (!trow) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) v[c] += s_bias[c];
+        }
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          const float val = v[c] + s_bias[c];
-          v[c] = val;
+          const float val = v[c];
           const float sv = valid ? val : 0.f;
           gs[c / GS] += sv;
           gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+          if (p.ex.act) v[c] = swishf(val);
+        }
+        uint4 o[COUT / 8];
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 8) {
+          o[c0 / 8].x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
+          o[c0 / 8].y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
+          o[c0 / 8].z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
+          o[c0 / 8].w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
         }
         if (valid && !(p.variant & 8)) {
 #pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
-            o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
-            o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
-            o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
-            *reinterpret_cast<uint4*>(yrow + c0) = o;
+          for (int c0 = 0; c0 < COUT; c0 += 8) *reinterpret_cast<uint4*>(yrow + c0) = o[c0 / 8];
+        }
+        if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
+#pragma unroll
+          for (int b = 0; b < NCS; ++b) {
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int c = b * 32 + i;
+              float2 f = make_float2(0.f, 0.f);
+              if (c < COUT) {
+                const uint4& q = o[c / 8];
+                const uint32_t wd = ((c % 8) / 2) == 0 ? q.x : (((c % 8) / 2) == 1 ? q.y : (((c % 8) / 2) == 2 ? q.z : q.w));
+                f = unpack_bf16x2(wd);
+              }
+              t[i] = valid ? f.x : 0.f;
+              t[i + 1] = valid ? f.y : 0.f;
+            }
+            csum[b] += warp_transpose_sum32(t, lane);
           }
         }
+      }
+      if (p.ex.chan_sum) {
+#pragma unroll
+        for (int b = 0; b < NCS; ++b)
+          if (b * 32 + lane < COUT) atomicAdd(p.ex.chan_sum + size_t(it.n) * COUT + b * 32 + lane, csum[b]);
       }
       if (p.stats) {
 #pragma unroll
@@ -331,10 +394,14 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
 
 // ------------------------------------------------------------------------------------------ weight repack
 // out = shared-memory image: [tap9 = kh*3+kw][kc][ng = 3*cout/8][8 n][8 k] bf16, n = j*cout + co with kd = 2 - j.
+// scale != NULL: per-sample copies (blockIdx.y = sample) with the input channels multiplied by scale[sample][ci].
 __global__ void pack_march_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
-                                         int cin_o, int rows, int kc, int transpose_flip) {
+                                         int cin_o, int rows, int kc, int transpose_flip,
+                                         const float* __restrict__ scale = nullptr, int ldscale = 0) {
   const int ng = 3 * rows / 8;
   const size_t total = size_t(9) * kc * ng * 64;
+  out += size_t(blockIdx.y) * total;
+  if (scale) scale += size_t(blockIdx.y) * ldscale;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
     size_t t = i >> 6;
@@ -345,7 +412,7 @@ __global__ void pack_march_weight_kernel(const float* __restrict__ w, __nv_bfloa
     const int ki = c * 8 + k8;
     float v = 0.f;
     if (!transpose_flip) {
-      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + (kd * 9 + kh * 3 + kw)];
+      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + (kd * 9 + kh * 3 + kw)] * (scale ? scale[ki] : 1.f);
     } else {
       // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
       if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + ((2 - kd) * 9 + (2 - kh) * 3 + (2 - kw))];
@@ -392,6 +459,21 @@ extern "C" int b21_pack_conv_weight_march(const float* w, void* packed, int cout
   return B21_OK;
 }
 
+// Per-sample folded packing: packed[s] = pack(w * scale[s][ci]) for s < nsamples, b21_conv_march_weight_bytes apart.
+extern "C" int b21_pack_conv_weight_march_fold(const float* w, void* packed, int cout, int cin, const float* scale,
+                                               int ldscale, int nsamples, void* stream) {
+  B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_march_fold: bad args");
+  B21_CHECK_ARG(cout % 8 == 0, "pack_conv_weight_march_fold: output channels %d must be a multiple of 8", cout);
+  const int kc = march_kc(cin);
+  const size_t total = march_wbytes(cin, cout) / 2;
+  const int threads = 256;
+  const int bx = int((total + threads - 1) / threads) < 512 ? int((total + threads - 1) / threads) : 512;
+  pack_march_weight_kernel<<<dim3(bx, nsamples), threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, kc, 0, scale, ldscale);
+  B21_LAUNCH_CHECK("pack_march_weight_kernel(fold)");
+  return B21_OK;
+}
+
 template <int COUT>
 static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
                         cudaStream_t stream) {
@@ -406,8 +488,31 @@ static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t 
   return B21_OK;
 }
 
+static int march_fwd_impl(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
+                          double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
+                          void* stream_);
+
 extern "C" int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                                     double* stats, int n, int d, int h, int w, int cin, int cout, void* stream_) {
+  FoldExtras ex = {nullptr, nullptr, 0, 0};
+  return march_fwd_impl(x, ldx, w_march, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_);
+}
+
+// Folded-EvoNorm variant (see fold.cu): per-sample weights `wstride_n` bytes apart (0 = shared), bias table
+// [n][27][cout] instead of a bias (or NULL -> plain `bias`), optional swish before the store, optional channel sums.
+extern "C" int b21_conv3d_march_fwd_fold(const void* x, int ldx, const void* w_march, long long wstride_n,
+                                         const float* bias, const float* bias_table, void* y, int ldy, double* stats,
+                                         float* chan_sum, int act, int n, int d, int h, int w, int cin, int cout,
+                                         void* stream_) {
+  B21_CHECK_ARG(!bias_table || (d >= 2 && h >= 2 && w >= 2), "conv3d_march_fwd_fold: border classes need dims >= 2");
+  B21_CHECK_ARG(wstride_n >= 0 && wstride_n % 16 == 0, "conv3d_march_fwd_fold: weight stride must be a multiple of 16 B");
+  FoldExtras ex = {bias_table, chan_sum, wstride_n, act};
+  return march_fwd_impl(x, ldx, w_march, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_);
+}
+
+static int march_fwd_impl(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
+                          double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B21_CHECK_ARG(x && w_march && y, "conv3d_march_fwd: null pointer");
   B21_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0, "conv3d_march_fwd: bad shape %d %d %d %d", n, d, h, w);
@@ -429,6 +534,7 @@ extern "C" int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march,
   p.stages = march_stages(cin, cout);
   p.ring = 512 / cout < kMMaxRing ? 512 / cout : kMMaxRing;
   p.wbytes = (uint32_t)march_wbytes(cin, cout);
+  p.ex = ex;
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("B21_MARCH_VARIANT");

@@ -16,6 +16,7 @@
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 #include "ptx.cuh"
+#include "fold.cuh"
 #include "host_common.h"
 
 namespace b21 {
@@ -32,6 +33,7 @@ struct ConvPointParams {
   int N, Cin, ldy;
   long long nvox;      // voxels per sample
   int tiles_per_n, tiles, chunks, stages;
+  FoldExtras ex;  // table = per-sample bias [N][Cout]; wstride != 0: per-sample weights (third coordinate of tmB)
 };
 
 template <int COUT>
@@ -86,13 +88,24 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(&w_bar, uint32_t(p.chunks) * BN * 128);
-      for (int ck = 0; ck < p.chunks; ++ck) tma_load_3d(sB + size_t(ck) * BN * 128, &tmB, &w_bar, ck * 64, 0, 0);
       int s = 0;
       uint32_t ph = 0;
+      int w_n = -1;
       for (int tile = t_begin; tile < t_end; ++tile) {
         const int n = tile / p.tiles_per_n;
         const int r0 = (tile - n * p.tiles_per_n) * 128;
+        if (w_n < 0 || (p.ex.wstride != 0 && n != w_n)) {
+          if (w_n >= 0) {  // every activation stage released <=> every MMA that read the old weights has completed
+            for (int k = 0; k < p.stages; ++k) {
+              const int s2 = s + k < p.stages ? s + k : s + k - p.stages;
+              mbar_wait(&empty_bar[s2], (s + k < p.stages ? ph : ph ^ 1) ^ 1);
+            }
+          }
+          w_n = n;
+          mbar_expect_tx(&w_bar, uint32_t(p.chunks) * BN * 128);
+          for (int ck = 0; ck < p.chunks; ++ck)
+            tma_load_3d(sB + size_t(ck) * BN * 128, &tmB, &w_bar, ck * 64, 0, p.ex.wstride != 0 ? n : 0);
+        }
         for (int ck = 0; ck < p.chunks; ++ck) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], kPtABytes);
@@ -108,12 +121,19 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN);
       const uint32_t b_addr = smem_u32(sB), a_addr = smem_u32(sA);
-      mbar_wait(&w_bar, 0);
-      tc_fence_after();
       int s = 0;
       uint32_t ph = 0;
       uint32_t it = 0;
+      int w_n = -1;
+      uint32_t w_par = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int n = tile / p.tiles_per_n;
+        if (w_n < 0 || (p.ex.wstride != 0 && n != w_n)) {
+          w_n = n;
+          mbar_wait(&w_bar, w_par);
+          w_par ^= 1u;
+          tc_fence_after();
+        }
         const uint32_t buf = it & 1u;
         mbar_wait(&acce_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -180,13 +200,14 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acce_bar[buf]);
+      const float* tb = p.ex.table ? p.ex.table + size_t(n) * COUT : nullptr;
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
-        const float val = v[c] + s_bias[c];
-        v[c] = val;
+        const float val = v[c] + (tb ? __ldg(tb + c) : s_bias[c]);
         const float sv = valid ? val : 0.f;
         gs[c / GS] += sv;
         gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+        v[c] = p.ex.act ? swishf(val) : val;
       }
       if (valid) {
         __nv_bfloat16* yrow = p.y + (size_t(n) * p.nvox + r) * size_t(p.ldy);
@@ -240,8 +261,26 @@ extern "C" int b21_conv_point_supported(int cin, int cout) {
   return point_stages(cin, cout) >= 3 ? 1 : 0;
 }
 
+static int point_fwd_impl(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
+                          double* stats, int n, long long nvox, int cin, int cout, const FoldExtras& ex, void* stream_);
+
 extern "C" int b21_conv1x1_fwd(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
                                double* stats, int n, long long nvox, int cin, int cout, void* stream_) {
+  FoldExtras ex = {nullptr, nullptr, 0, 0};
+  return point_fwd_impl(x, ldx, w_packed, bias, y, ldy, stats, n, nvox, cin, cout, ex, stream_);
+}
+
+// Folded-EvoNorm variant (see fold.cu): `per_sample` != 0 -> w_packed holds n weight sets (b21_pack_conv_weight_fold),
+// bias_n (or NULL -> `bias`) is a per-sample bias [n][cout]; act != 0 stores x*sigmoid(x).
+extern "C" int b21_conv1x1_fwd_fold(const void* x, int ldx, const void* w_packed, int per_sample, const float* bias,
+                                    const float* bias_n, void* y, int ldy, double* stats, int act, int n,
+                                    long long nvox, int cin, int cout, void* stream_) {
+  FoldExtras ex = {bias_n, nullptr, per_sample ? 1 : 0, act};
+  return point_fwd_impl(x, ldx, w_packed, bias, y, ldy, stats, n, nvox, cin, cout, ex, stream_);
+}
+
+static int point_fwd_impl(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
+                          double* stats, int n, long long nvox, int cin, int cout, const FoldExtras& ex, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B21_CHECK_ARG(x && w_packed && y, "conv1x1_fwd: null pointer");
   B21_CHECK_ARG(n > 0 && nvox > 0 && nvox < (1ll << 31), "conv1x1_fwd: bad shape n %d nvox %lld", n, nvox);
@@ -259,6 +298,7 @@ extern "C" int b21_conv1x1_fwd(const void* x, int ldx, const void* w_packed, con
   p.tiles = p.tiles_per_n * n;
   p.chunks = (cin + 63) / 64;
   p.stages = point_stages(cin, cout);
+  p.ex = ex;
   const int bn = point_bn(cout);
 
   CUtensorMap tmA, tmB;
@@ -271,7 +311,7 @@ extern "C" int b21_conv1x1_fwd(const void* x, int ldx, const void* w_packed, con
   }
   {
     // packed weight of b21_pack_conv_weight(k = 1): [1][cout_padded = bn][cin]
-    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)bn, 1};
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)bn, (uint64_t)(ex.wstride != 0 ? n : 1)};
     const uint64_t str[2] = {uint64_t(cin) * 2, uint64_t(bn) * cin * 2};
     const uint32_t box[3] = {64, (uint32_t)bn, 1};
     int r = encode_tmap_bf16(&tmB, w_packed, 3, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_128B);

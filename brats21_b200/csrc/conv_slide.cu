@@ -26,6 +26,7 @@
 // for 16 <= Cin <= 96, Cout a multiple of the N tile (48 or 96), and is reused for the data gradient with the
 // transposed + mirrored packing.
 #include "ptx.cuh"
+#include "fold.cuh"
 #include "host_common.h"
 #include <stdlib.h>
 
@@ -51,6 +52,7 @@ struct ConvSlideParams {
   int tilesH, tilesW, segs, L, ntiles, items;
   int pslots, wstages, wsub, ks_sub;
   uint32_t tap_bytes, wstage_bytes;
+  FoldExtras ex;
   int variant;  // debug (B21_SLIDE_VARIANT): bit0 no plane loads, bit1 no weight loads, bit2 no epilogue math/stores, bit3 one MMA per stage
 };
 
@@ -162,7 +164,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const SlideItem it = slide_decode(p, item);
         const int G = (it.Lc + 2) / 3;
-        const uint8_t* wt = p.wpk + size_t(it.nt) * 27 * p.tap_bytes;
+        const uint8_t* wt = p.wpk + size_t(p.ex.wstride) * it.n + size_t(it.nt) * 27 * p.tap_bytes;
         for (int g = 0; g < G; ++g) {
           for (int tap = 0; tap < 27; ++tap) {  // tap = kd * 9 + kh * 3 + kw: phase kd walks taps kd*9 .. kd*9+8
             for (int sub = 0; sub < kWsub; ++sub) {
@@ -332,6 +334,14 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy) + cbase;
       const size_t ystep = size_t(p.H) * p.W * p.ldy;
       const float* bias = p.bias ? p.bias + cbase : nullptr;
+      const int cout_all = p.ntiles * NT;
+      const float* trow = p.ex.table ? p.ex.table + (size_t(it.n) * 27 + border_class(h, p.H) * 3 + border_class(w, p.W)) *
+                                                          cout_all + cbase
+                                     : nullptr;
+      constexpr int NCS = (NT + 31) / 32;
+      float csum[NCS];  // lane l: running sum of the stored outputs of channels l, 32 + l, ...
+#pragma unroll
+      for (int b = 0; b < NCS; ++b) csum[b] = 0.f;
       for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
         mbar_wait_a(accf0 + 8u * slot, par);
         tc_fence_after();
@@ -347,25 +357,57 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           par ^= 1u;
         }
         if (p.variant & 4) continue;
+        if (trow) {  // folded input affine: the bias depends on the border class of the output voxel
+          if (valid) {
+            const float4* tb =
+                reinterpret_cast<const float4*>(trow + size_t(border_class(it.d0 + so, p.D)) * 9 * cout_all);
+#pragma unroll
+            for (int c4 = 0; c4 < NT / 4; ++c4) {
+              const float4 t4 = __ldg(tb + c4);
+              v[c4 * 4 + 0] += t4.x; v[c4 * 4 + 1] += t4.y; v[c4 * 4 + 2] += t4.z; v[c4 * 4 + 3] += t4.w;
+            }
+          }
+        } else if (bias) {
+#pragma unroll
+          for (int c = 0; c < NT; ++c) v[c] += __ldg(bias + c);
+        }
 #pragma unroll
         for (int c = 0; c < NT; ++c) {
-          const float val = v[c] + (bias ? __ldg(bias + c) : 0.f);
-          v[c] = val;
+          const float val = v[c];
           const float sv = valid ? val : 0.f;
           gs[c / GS] += sv;
           gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+          if (p.ex.act) v[c] = swishf(val);
         }
+        uint32_t o[NT / 2];
+#pragma unroll
+        for (int c = 0; c < NT; c += 2) o[c / 2] = pack_bf16x2(v[c], v[c + 1]);
         if (valid) {
 #pragma unroll
-          for (int c0 = 0; c0 < NT; c0 += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
-            o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
-            o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
-            o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
-            *reinterpret_cast<uint4*>(yrow + c0) = o;
+          for (int c0 = 0; c0 < NT; c0 += 8)
+            *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(o[c0 / 2], o[c0 / 2 + 1], o[c0 / 2 + 2], o[c0 / 2 + 3]);
+        }
+        if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
+#pragma unroll
+          for (int b = 0; b < NCS; ++b) {
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int c = b * 32 + i;
+              float2 f = make_float2(0.f, 0.f);
+              if (c < NT) f = unpack_bf16x2(o[c / 2]);
+              t[i] = valid ? f.x : 0.f;
+              t[i + 1] = valid ? f.y : 0.f;
+            }
+            csum[b] += warp_transpose_sum32(t, lane);
           }
         }
+      }
+      if (p.ex.chan_sum) {
+#pragma unroll
+        for (int b = 0; b < NCS; ++b)
+          if (b * 32 + lane < NT)
+            atomicAdd(p.ex.chan_sum + size_t(it.n) * cout_all + cbase + b * 32 + lane, csum[b]);
       }
       if (p.stats) {
 #pragma unroll
@@ -396,11 +438,15 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
 
 // ------------------------------------------------------------------------------------------ weight repack
 // out = UMMA shared-memory image per (N tile, tap): [ntile][tap = kd*9+kh*3+kw][kc][NT/8][8 n][8 k] bf16.
+// scale != NULL: per-sample copies (blockIdx.y = sample) with the input channels multiplied by scale[sample][ci].
 __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
-                                         int cin_o, int rows, int kc, int nt, int transpose_flip) {
+                                         int cin_o, int rows, int kc, int nt, int transpose_flip,
+                                         const float* __restrict__ scale = nullptr, int ldscale = 0) {
   const int ng = nt / 8;
   const int ntiles = rows / nt;
   const size_t total = size_t(ntiles) * 27 * kc * ng * 64;
+  out += size_t(blockIdx.y) * total;
+  if (scale) scale += size_t(blockIdx.y) * ldscale;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
     size_t t = i >> 6;
@@ -412,7 +458,7 @@ __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloa
     const int ki = c * 8 + k8;
     float v = 0.f;
     if (!transpose_flip) {
-      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap];
+      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap] * (scale ? scale[ki] : 1.f);
     } else {  // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
       if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + (26 - tap)];
     }
@@ -510,8 +556,44 @@ extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout
   return B21_OK;
 }
 
+extern "C" int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int cout, int cin, const float* scale,
+                                               int ldscale, int nsamples, void* stream) {
+  B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_slide_fold: bad args");
+  SlideCfg c;
+  B21_CHECK_ARG(slide_config(cin, cout, &c), "pack_conv_weight_slide_fold: (cin %d, cout %d) unsupported", cin, cout);
+  const size_t total = size_t(27) * c.kc * cout * 8;
+  const int threads = 256;
+  const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
+  pack_slide_weight_kernel<<<dim3(bx, nsamples), threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale);
+  B21_LAUNCH_CHECK("pack_slide_weight_kernel(fold)");
+  return B21_OK;
+}
+
+static int slide_fwd_impl(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
+                          double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
+                          void* stream_);
+
 extern "C" int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
                                     double* stats, int n, int d, int h, int w, int cin, int cout, void* stream_) {
+  FoldExtras ex = {nullptr, nullptr, 0, 0};
+  return slide_fwd_impl(x, ldx, w_slide, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_);
+}
+
+// Folded-EvoNorm variant (see fold.cu); arguments as b21_conv3d_march_fwd_fold.
+extern "C" int b21_conv3d_slide_fwd_fold(const void* x, int ldx, const void* w_slide, long long wstride_n,
+                                         const float* bias, const float* bias_table, void* y, int ldy, double* stats,
+                                         float* chan_sum, int act, int n, int d, int h, int w, int cin, int cout,
+                                         void* stream_) {
+  B21_CHECK_ARG(!bias_table || (d >= 2 && h >= 2 && w >= 2), "conv3d_slide_fwd_fold: border classes need dims >= 2");
+  B21_CHECK_ARG(wstride_n >= 0 && wstride_n % 16 == 0, "conv3d_slide_fwd_fold: weight stride must be a multiple of 16 B");
+  FoldExtras ex = {bias_table, chan_sum, wstride_n, act};
+  return slide_fwd_impl(x, ldx, w_slide, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_);
+}
+
+static int slide_fwd_impl(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
+                          double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B21_CHECK_ARG(x && w_slide && y, "conv3d_slide_fwd: null pointer");
   B21_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0, "conv3d_slide_fwd: bad shape %d %d %d %d", n, d, h, w);
@@ -534,6 +616,7 @@ extern "C" int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide,
   p.ntiles = cout / c.nt;
   p.pslots = c.pslots; p.wstages = c.wstages; p.wsub = c.wsub; p.ks_sub = c.ks_sub;
   p.tap_bytes = c.tap_bytes; p.wstage_bytes = c.wstage_bytes;
+  p.ex = ex;
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("B21_SLIDE_VARIANT");

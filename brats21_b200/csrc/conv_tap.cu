@@ -197,16 +197,20 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------- weight repack
+// scale != NULL: per-sample copies (blockIdx.y = sample) with the input channels multiplied by scale[sample][ci].
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
-                                        int cin, int rows_padded, int inner_padded, int T, int transpose_flip) {
+                                        int cin, int rows_padded, int inner_padded, int T, int transpose_flip,
+                                        const float* __restrict__ scale = nullptr, int ldscale = 0) {
   const size_t total = size_t(T) * rows_padded * inner_padded;
+  out += size_t(blockIdx.y) * total;
+  if (scale) scale += size_t(blockIdx.y) * ldscale;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int ki = int(i % inner_padded);
     const int r = int((i / inner_padded) % rows_padded);
     const int tap = int(i / (size_t(inner_padded) * rows_padded));
     float v = 0.f;
     if (!transpose_flip) {
-      if (r < cout && ki < cin) v = w[(size_t(r) * cin + ki) * T + tap];
+      if (r < cout && ki < cin) v = w[(size_t(r) * cin + ki) * T + tap] * (scale ? scale[ki] : 1.f);
     } else {
       // rows = original input channels, inner = original output channels, taps mirrored
       if (r < cin && ki < cout) v = w[(size_t(ki) * cin + r) * T + (T - 1 - tap)];
@@ -251,6 +255,23 @@ extern "C" int b21_pack_conv_weight(const float* w, void* packed, int cout, int 
   pack_conv_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, transpose_flip);
   B21_LAUNCH_CHECK("pack_conv_weight_kernel");
+  return B21_OK;
+}
+
+// Per-sample folded packing (k = 1 or 3): packed[s] = pack(w * scale[s][ci]), taps*cout_padded*cin_padded bf16 apart.
+extern "C" int b21_pack_conv_weight_fold(const float* w, void* packed, int cout, int cin, int cin_padded, int k,
+                                         const float* scale, int ldscale, int nsamples, void* stream) {
+  B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_fold: bad args");
+  B21_CHECK_ARG(k == 1 || k == 3, "pack_conv_weight_fold: k must be 1 or 3 (got %d)", k);
+  B21_CHECK_ARG(cin_padded >= cin && cin_padded % 8 == 0, "pack_conv_weight_fold: bad inner padding");
+  const int T = k * k * k;
+  const int rows_padded = b21_conv_cout_padded(cout);
+  const size_t total = size_t(T) * rows_padded * cin_padded;
+  const int threads = 256;
+  const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
+  pack_conv_weight_kernel<<<dim3(bx, nsamples), threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, 0, scale, ldscale);
+  B21_LAUNCH_CHECK("pack_conv_weight_kernel(fold)");
   return B21_OK;
 }
 

@@ -306,23 +306,32 @@ __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------ 1x1 head conv
-// logits[n][k][vox] = b[k] + sum_c w[k][c] * scale[n][c] * x[n][vox][c];  K <= 4, C <= 512
+// logits[n][k][vox] = b[k] + sum_c w[k][c] * (scale[n][c] * x[n][vox][c] + offset[n][c]);  K <= 4, C <= 1024
+// (scale / offset = the folded affine of the input: SE gate, or EvoNorm (A, B) of the folded inference path)
 template <int K>
 __global__ void __launch_bounds__(256) head_conv_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                         const float* __restrict__ scale,
+                                                        const float* __restrict__ offset, int ldso,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         float* __restrict__ out, int N, long long nvox, int C) {
-  extern __shared__ float sw[];  // [K][C] (pre-scaled per n)
+  extern __shared__ float sw[];  // [K][C] (pre-scaled per n), then [K] biases
+  float* sb = sw + K * C;
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < K * C; i += blockDim.x)
-    sw[i] = w[i] * (scale ? scale[size_t(n) * C + (i % C)] : 1.f);
+    sw[i] = w[i] * (scale ? scale[size_t(n) * ldso + (i % C)] : 1.f);
+  if (threadIdx.x < K) {
+    float s = b ? b[threadIdx.x] : 0.f;
+    if (offset)
+      for (int c = 0; c < C; ++c) s = fmaf(w[threadIdx.x * C + c], offset[size_t(n) * ldso + c], s);
+    sb[threadIdx.x] = s;
+  }
   __syncthreads();
   const __nv_bfloat16* xn = x + size_t(n) * nvox * ldx;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox;
        v += (long long)gridDim.x * blockDim.x) {
     float acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = b ? __ldg(b + k) : 0.f;
+    for (int k = 0; k < K; ++k) acc[k] = sb[k];
     const __nv_bfloat16* xv = xn + v * ldx;
     for (int c = 0; c < C; c += 8) {
       float f[8];
@@ -419,18 +428,19 @@ extern "C" int b21_upsample_f32(const float* x, float* y, int planes, int d, int
   return B21_OK;
 }
 
-extern "C" int b21_head_conv(const void* x, int ldx, const float* scale, const float* w, const float* b, float* out,
+extern "C" int b21_head_conv(const void* x, int ldx, const float* scale, const float* offset, int ldso, const float* w,
+                             const float* b, float* out,
                              int n, long long nvox, int c, int k, void* stream) {
   B21_CHECK_ARG(x && w && out, "head_conv: null pointer");
   B21_CHECK_ARG(k >= 1 && k <= 4 && c % 8 == 0 && c <= 1024, "head_conv: K must be 1..4 and C a multiple of 8");
   dim3 grid(grid_for(nvox, 256), n);
-  const size_t smem = sizeof(float) * k * c;
+  const size_t smem = sizeof(float) * (k * c + k);
   cudaStream_t st = (cudaStream_t)stream;
   switch (k) {
-    case 1: head_conv_kernel<1><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
-    case 2: head_conv_kernel<2><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
-    case 3: head_conv_kernel<3><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
-    default: head_conv_kernel<4><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, b, out, n, nvox, c); break;
+    case 1: head_conv_kernel<1><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, offset, ldso, w, b, out, n, nvox, c); break;
+    case 2: head_conv_kernel<2><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, offset, ldso, w, b, out, n, nvox, c); break;
+    case 3: head_conv_kernel<3><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, offset, ldso, w, b, out, n, nvox, c); break;
+    default: head_conv_kernel<4><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, offset, ldso, w, b, out, n, nvox, c); break;
   }
   B21_LAUNCH_CHECK("head_conv_kernel");
   return B21_OK;

@@ -414,9 +414,103 @@ class EquiUnetASSPEvo(_B21Net):
         ops.norm_apply(out, stats, p[name + ".g"], p[name + ".b"], ops.EVO_S0)
         return out
 
+    # ---- folded-EvoNorm inference path (csrc/fold.cu): levels 1-2 never run a normalisation pass
+    _FOLD_CONVS = ["encoder1.c0", "encoder1.c1", "encoder2.c0", "encoder2.c1", "decoder2.c0", "decoder2.c1",
+                   "decoder1.c0", "decoder1.c1", "bridge1", "bridge2", "upconv1", "upconv2"]
+
+    def _fold_ok(self, d, h, w):
+        return ops.use_fold and min(h, w) >= 16 and d >= 4 and all(ops.fold_supported(self._packed[k])
+                                                                    for k in self._FOLD_CONVS)
+
+    def _ab(self, ws, name, n, c):
+        t = self._buf(ws, name, (2, n, c), torch.float32)
+        return t[0], t[1]
+
+    def _fblock(self, name, x, xab, tmp, out, stats, csum, ab_tmp, ab_out):
+        """ConvEvoBlockCorrected on stored-swish tensors: conv -> S0 (+stats) ; conv(fold a0,b0) -> S1 (+stats, channel
+        sums) ; (A, B) of the block output = EvoNorm affine x SE gate."""
+        p = self._packed
+        n, d, h, w, _ = out.shape
+        nvox = d * h * w
+        ops.conv3d_fold(x, p[name + ".c0"], tmp, stats, ab=xab, act=True)
+        ops.evo_se_affine(stats, p[name + ".e0.g"], p[name + ".e0.b"], ab_tmp[0], ab_tmp[1], nvox)
+        csum.zero_()
+        ops.conv3d_fold(tmp, p[name + ".c1"], out, stats, ab=ab_tmp, act=True, chan_sum=csum)
+        ops.evo_se_affine(stats, p[name + ".e1.g"], p[name + ".e1.b"], ab_out[0], ab_out[1], nvox, chan_sum=csum,
+                          se=(p[name + ".se.w1"], p[name + ".se.b1"], p[name + ".se.w2"], p[name + ".se.b2"]))
+
+    def _fconvevo(self, name, x, xab, out, stats, ab_out):
+        """ConvEvo (1x1) on a stored-swish input; output stored as swish, its EvoNorm affine written to ab_out."""
+        p = self._packed
+        n, d, h, w, _ = out.shape
+        ops.conv3d_fold(x, p[name], out, stats, ab=xab, act=True)
+        ops.evo_se_affine(stats, p[name + ".g"], p[name + ".b"], ab_out[0], ab_out[1], d * h * w)
+
+    def forward_packed_folded(self, x8: torch.Tensor, want_deep: bool = True):
+        n, d, h, w, _ = x8.shape
+        f = self.features
+        ws = self._ws.setdefault(("v2f", n, d, h, w), {})
+        B = lambda name, s, c: self._buf(ws, name, (n, d // s, h // s, w // s, c))  # noqa: E731
+        stats = self._buf(ws, "stats", (ops._lib.STAT_SLOTS, n, 8, 2), torch.float64)
+        cs = [self._buf(ws, f"csum{i}", (n, f[i]), torch.float32) for i in range(4)]
+        t1, t2, t3, t4 = B("t1", 1, f[0]), B("t2", 2, f[1]), B("t3", 4, f[2]), B("t4", 8, f[3])
+        d1, d2, d3, d4 = B("d1", 1, f[0]), B("d2", 2, f[1]), B("d3", 4, f[2]), B("d4", 8, f[3])
+        p1, p2, p3 = B("p1", 2, 2 * f[0]), B("p2", 4, 2 * f[1]), B("p3", 8, 2 * f[2])
+        cat1, cat2, cat3 = B("cat1", 1, f[0]), B("cat2", 2, f[1]), B("cat3", 4, f[2])
+        ab_t1, ab_t2 = self._ab(ws, "ab_t1", n, f[0]), self._ab(ws, "ab_t2", n, f[1])
+        ab_d1, ab_d2 = self._ab(ws, "ab_d1", n, f[0]), self._ab(ws, "ab_d2", n, f[1])
+        ab_c1, ab_c2 = self._ab(ws, "ab_c1", n, f[0]), self._ab(ws, "ab_c2", n, f[1])
+        ab_u1, ab_u2 = self._ab(ws, "ab_u1", n, f[0]), self._ab(ws, "ab_u2", n, f[1])
+        h0, h1 = f[0] // 2, f[1] // 2
+
+        # levels 1-2 of the encoder: stored-swish tensors, pooled outputs are actual values
+        self._fblock("encoder1", x8, None, t1, d1, stats, cs[0], ab_t1, ab_d1)
+        ops.affine_pool(d1, ab_d1[0], ab_d1[1], p1, mode=2)
+        self._fblock("encoder2", p1, None, t2, d2, stats, cs[1], ab_t2, ab_d2)
+        ops.affine_pool(d2, ab_d2[0], ab_d2[1], p2, mode=2)
+        # levels 3-4: explicit normalisation (tap kernel; < 4 % of the elementwise traffic)
+        _, s = self._block("encoder3", p2, t3, d3, stats, cs[2])
+        ops.scale_pool(d3, s, full=d3, pooled=p3, mode=2)
+        _, s = self._block("encoder4", p3, t4, d4, stats, cs[3])
+        ops.scale_pool(d4, s, full=d4, mode=0)
+        pk = self._packed
+        acat = B("asppcat", 8, f[3])
+        q = f[3] // 4
+        for i, dil in enumerate(self.aspp.dilations):
+            ops.conv3d(d4, pk[f"aspp.convs.{i}"], out=acat[..., i * q:(i + 1) * q], dil=dil)
+        assp = self._convevo("aspp.conv_k1", acat, t4, stats)
+
+        self._fconvevo("bridge1", d1, ab_d1, cat1[..., :h0], stats, (ab_c1[0][:, :h0], ab_c1[1][:, :h0]))
+        self._fconvevo("bridge2", d2, ab_d2, cat2[..., :h1], stats, (ab_c2[0][:, :h1], ab_c2[1][:, :h1]))
+        self._convevo("bridge3", d3, cat3[..., :f[2] // 2], stats)
+
+        u = self._convevo("upconv3", assp, B("uc3", 8, f[3] // 4), stats)
+        ops.upsample2x(u, cat3[..., f[2] // 2:])
+        up3, s = self._block("decoder3", cat3, t3, B("up3", 4, f[2]), stats, cs[2])
+        ops.scale_pool(up3, s, full=up3, mode=0)
+        uc2 = B("uc2", 4, f[2] // 4)
+        self._fconvevo("upconv2", up3, None, uc2, stats, (ab_c2[0][:, h1:], ab_c2[1][:, h1:]))
+        ops.upsample2x(uc2, cat2[..., h1:])  # interpolation weights sum to 1: the affine passes through unchanged
+        up2 = B("up2", 2, f[1])
+        self._fblock("decoder2", cat2, ab_c2, t2, up2, stats, cs[1], ab_t2, ab_u2)
+        uc1 = B("uc1", 2, f[1] // 4)
+        self._fconvevo("upconv1", up2, ab_u2, uc1, stats, (ab_c1[0][:, h0:], ab_c1[1][:, h0:]))
+        ops.upsample2x(uc1, cat1[..., h0:])
+        up1 = B("up1", 1, f[0])
+        self._fblock("decoder1", cat1, ab_c1, t1, up1, stats, cs[0], ab_t1, ab_u1)
+        out = ops.head_conv(up1, pk["out_conv.w"], pk["out_conv.bias"], scale=ab_u1[0], offset=ab_u1[1])
+        deeps: List[torch.Tensor] = []
+        if want_deep and self.deep_supervision:
+            deeps.append(ops.upsample_f32(ops.head_conv(up3, pk["deep3.0.w"], pk["deep3.0.bias"]), 4))
+            deeps.append(ops.upsample_f32(ops.head_conv(up2, pk["deep2.0.w"], pk["deep2.0.bias"], scale=ab_u2[0],
+                                                        offset=ab_u2[1]), 2))
+        return out, deeps
+
     def forward_packed(self, x8: torch.Tensor, want_deep: bool = True):
         self._ensure_packed()
         n, d, h, w, _ = x8.shape
+        if self._fold_ok(d, h, w):
+            return self.forward_packed_folded(x8, want_deep)
         f = self.features
         ws = self._ws.setdefault(("v2", n, d, h, w), {})
         B = lambda name, s, c: self._buf(ws, name, (n, d // s, h // s, w // s, c))  # noqa: E731

@@ -33,6 +33,7 @@ class PackedConv:
         self.cout_padded = _lib.load().b21_conv_cout_padded(rows)
         self.w = torch.empty((self.taps, self.cout_padded, cin_padded), dtype=torch.bfloat16, device=weight.device)
         w32 = weight.detach().to(torch.float32).contiguous()
+        self.w32, self.cin_padded, self._fold = w32, cin_padded, {}
         call("b21_pack_conv_weight", ptr(w32), ptr(self.w), cout, cin, cin_padded, k, int(transpose_flip),
              stream_ptr())
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
@@ -89,6 +90,99 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
     return out
 
 
+# ---------------------------------------------------------------------------------------------- folded EvoNorm
+def evo_se_affine(stats, gamma, beta, a_out, b_out, nvox, chan_sum=None, se=None, eps=1e-5):
+    """(A, B)[n][c] of EvoNorm-S0 [+ ResidualSE gate] from conv-epilogue statistics (see csrc/fold.cu).
+    a_out / b_out: fp32 [n, c] views (row stride = ld) that receive A and B.  se = (w1, b1, w2, b2)."""
+    n, c = a_out.shape
+    assert a_out.stride(1) == 1 and b_out.stride(1) == 1 and a_out.stride(0) == b_out.stride(0)
+    w1 = b1 = w2 = b2 = None
+    hidden = 0
+    if chan_sum is not None:
+        w1, b1, w2, b2 = se
+        hidden = w1.shape[0]
+    call("b21_evo_se_affine", ptr(stats), ptr(gamma), ptr(beta), ptr(chan_sum), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+         ptr(a_out), ptr(b_out), a_out.stride(0), n, c, hidden, nvox, eps, stream_ptr())
+
+
+def _fold_prepare(pw: "PackedConv", a_in, b_in):
+    """Per-sample packed weights W * A[n][ci] and the bias table bias + (border-class tap sums of W) . B[n]."""
+    n, cin = a_in.shape
+    assert cin == pw.cin_true == pw.cin and a_in.stride(1) == 1 and b_in.stride(0) == a_in.stride(0)
+    dev = pw.w32.device
+    f = pw._fold
+    ncls = 27 if pw.taps == 27 else 1
+    if "ws" not in f:
+        f["ws"] = torch.empty((ncls, cin, pw.cout), dtype=torch.float32, device=dev)
+        call("b21_border_weight_sums", ptr(pw.w32), ptr(f["ws"]), pw.cout, cin, pw.taps, stream_ptr())
+    key = ("buf", n)
+    if key not in f:
+        if pw.taps == 1:
+            nbytes = pw.cout_padded * pw.cin * 2
+        elif pw.w_march is not None:
+            nbytes = pw.w_march.numel() * 2
+        else:
+            nbytes = pw.w_slide.numel() * 2
+        f[key] = (torch.empty((n, nbytes // 2), dtype=torch.bfloat16, device=dev),
+                  torch.empty((n, ncls, pw.cout), dtype=torch.float32, device=dev))
+    packed, table = f[key]
+    ld = a_in.stride(0)
+    if pw.taps == 1:
+        call("b21_pack_conv_weight_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, pw.cin, 1, ptr(a_in), ld, n,
+             stream_ptr())
+    elif pw.w_march is not None:
+        call("b21_pack_conv_weight_march_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, stream_ptr())
+    else:
+        call("b21_pack_conv_weight_slide_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, stream_ptr())
+    call("b21_bias_table", ptr(f["ws"]), ptr(pw.bias), ptr(b_in), ld, ptr(table), n, pw.cout, cin, ncls, stream_ptr())
+    return packed, packed.stride(0) * 2, table
+
+
+def fold_supported(pw: "PackedConv") -> bool:
+    """True when conv3d_fold can run this conv (persistent 1x1, march or slide kernel)."""
+    return (pw.taps == 1 and pw.point_ok) or (pw.taps == 27 and (pw.w_march is not None or pw.w_slide is not None))
+
+
+def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=None):
+    """conv3d whose INPUT is a stored swish tensor S with the affine ab = (A, B) [n, cin] folded into per-sample
+    weights and a border-class bias table, and whose OUTPUT is stored as swish(conv + bias) (act) with the group
+    statistics (and optionally the per-channel sums of the stored values, for the SE squeeze)."""
+    n, d, h, w, cin = x.shape
+    assert x.dtype == torch.bfloat16 and cin == pw.cin and out.shape == (n, d, h, w, pw.cout)
+    if ab is None:
+        wts = pw.w if pw.taps == 1 else (pw.w_march if pw.w_march is not None else pw.w_slide)
+        wstride, table = 0, None
+    else:
+        wts, wstride, table = _fold_prepare(pw, ab[0], ab[1])
+    prof = conv_profile
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    if pw.taps == 1:
+        assert pw.point_ok and chan_sum is None
+        call("b21_conv1x1_fwd_fold", ptr(x), _ld(x), ptr(wts), int(wstride != 0), ptr(pw.bias), ptr(table), ptr(out),
+             _ld(out), ptr(stats), int(act), n, d * h * w, cin, pw.cout, stream_ptr())
+    else:
+        assert h >= 8 and w >= 8
+        name = "b21_conv3d_march_fwd_fold" if pw.w_march is not None else "b21_conv3d_slide_fwd_fold"
+        call(name, ptr(x), _ld(x), ptr(wts), wstride, ptr(pw.bias), ptr(table), ptr(out), _ld(out), ptr(stats),
+             ptr(chan_sum), int(act), n, d, h, w, cin, pw.cout, stream_ptr())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (cin, pw.cout, pw.taps, d)))
+    return out
+
+
+def affine_pool(x, a_in, b_in, pooled, mode=2):
+    """pooled = MaxAvgPool (mode 2) / MaxPool (mode 1) of (A[n][c] * x + B[n][c])."""
+    n, d, h, w, c = x.shape
+    assert a_in.shape == (n, c) and a_in.stride(0) == b_in.stride(0)
+    call("b21_affine_pool", ptr(x), _ld(x), ptr(a_in), ptr(b_in), a_in.stride(0), ptr(pooled), _ld(pooled), mode,
+         n, d, h, w, c, stream_ptr())
+    return pooled
+
+
 # When set to a list, every conv launch appends (start_event, end_event, algorithmic_flops, shape_key):
 # bench.py uses it to time the dominant kernel live with CUDA events on the launching stream.
 conv_profile = None
@@ -96,6 +190,8 @@ conv_profile = None
 use_march = True
 # sliding-window kernel (conv_slide.cu) for the k = 3 shapes whose weights do not fit the march kernel
 use_slide = True
+# folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations
+use_fold = True
 # persistent 1x1 kernel (conv_point.cu) for the shapes it supports
 use_point = True
 
@@ -144,14 +240,16 @@ def upsample_f32(x, s):
     return out
 
 
-def head_conv(x, weight, bias, scale=None, out=None):
-    """1x1 conv to <=4 classes; returns NCDHW fp32 logits.  weight fp32 [K, C]."""
+def head_conv(x, weight, bias, scale=None, out=None, offset=None):
+    """1x1 conv to <=4 classes of (x * scale[n] + offset[n]); returns NCDHW fp32 logits.  weight fp32 [K, C]."""
     n, d, h, w, c = x.shape
     k = weight.shape[0]
     if out is None:
         out = torch.empty((n, k, d, h, w), dtype=torch.float32, device=x.device)
-    call("b21_head_conv", ptr(x), _ld(x), ptr(scale), ptr(weight), ptr(bias), ptr(out), n, d * h * w, c, k,
-         stream_ptr())
+    ldso = scale.stride(0) if scale is not None else (offset.stride(0) if offset is not None else c)
+    assert offset is None or scale is None or offset.stride(0) == scale.stride(0)
+    call("b21_head_conv", ptr(x), _ld(x), ptr(scale), ptr(offset), ldso, ptr(weight), ptr(bias), ptr(out), n,
+         d * h * w, c, k, stream_ptr())
     return out
 
 

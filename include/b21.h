@@ -88,6 +88,40 @@ int b21_conv_point_supported(int cin, int cout);
 int b21_conv1x1_fwd(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
                     double* stats, int n, long long nvox, int cin, int cout, void* stream);
 
+/* ------------------------------------------------------------------------------ folded EvoNorm (inference)
+ * EvoNorm-S0 is y = x*sigmoid(x) * a_c + b_c where only the affine (a, b) depends on the global group statistics
+ * (networks/equiunet2021.py:48-52,95-105).  The *_fold conv entry points store S = swish(conv + bias) directly
+ * (act = 1) with the statistics, and the affine (A, B) [n][c] — including the ResidualSE gate (equiunet2021.py:204-205)
+ * — is folded into the consumer: per-sample packed weights W*A[n][ci] (b21_pack_conv_weight_*_fold) and a bias table
+ * T[n][border class][co] = bias + sum_ci B[n][ci] * (sum of the taps of W[co][ci] that stay inside the volume)
+ * (b21_border_weight_sums once per weight, b21_bias_table per forward; class = cd*9+ch*3+cw, c = 0 first voxel /
+ * 1 interior / 2 last voxel of the axis; one class for k = 1).  This removes every normalisation pass over HBM.
+ * chan_sum (fp32 [n][cout], zeroed by the caller) receives the channel sums of the stored outputs (SE squeeze). */
+int b21_evo_se_affine(const double* stats, const float* gamma, const float* beta, const float* chan_sum,
+                      const float* w1, const float* b1, const float* w2, const float* b2, float* a_out, float* b_out,
+                      int ldab, int n, int c, int hidden, long long nvox, float eps, void* stream);
+int b21_border_weight_sums(const float* w, float* ws, int cout, int cin, int taps, void* stream);
+int b21_bias_table(const float* ws, const float* bias, const float* b_in, int ldab, float* table, int n, int cout,
+                   int cin, int ncls, void* stream);
+int b21_pack_conv_weight_fold(const float* w, void* packed, int cout, int cin, int cin_padded, int k,
+                              const float* scale, int ldscale, int nsamples, void* stream);
+int b21_pack_conv_weight_march_fold(const float* w, void* packed, int cout, int cin, const float* scale, int ldscale,
+                                    int nsamples, void* stream);
+int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int cout, int cin, const float* scale, int ldscale,
+                                    int nsamples, void* stream);
+int b21_conv3d_march_fwd_fold(const void* x, int ldx, const void* w_march, long long wstride_n, const float* bias,
+                              const float* bias_table, void* y, int ldy, double* stats, float* chan_sum, int act,
+                              int n, int d, int h, int w, int cin, int cout, void* stream);
+int b21_conv3d_slide_fwd_fold(const void* x, int ldx, const void* w_slide, long long wstride_n, const float* bias,
+                              const float* bias_table, void* y, int ldy, double* stats, float* chan_sum, int act,
+                              int n, int d, int h, int w, int cin, int cout, void* stream);
+int b21_conv1x1_fwd_fold(const void* x, int ldx, const void* w_packed, int per_sample, const float* bias,
+                         const float* bias_n, void* y, int ldy, double* stats, int act, int n, long long nvox, int cin,
+                         int cout, void* stream);
+/* MONAI MaxAvgPool (mode 2: [max | mean], equiunet2021.py:261) or max-pool (mode 1) of A[n][c] * x + B[n][c]. */
+int b21_affine_pool(const void* x, int ldx, const float* a_in, const float* b_in, int ldab, void* pooled, int ldpool,
+                    int mode, int n, int d, int h, int w, int c, void* stream);
+
 /* ------------------------------------------------------------------------------------- normalisation / SE
  * norm_apply: y = GroupNorm(8,C)(x) -> ReLU (mode 0; networks/factory.py:182 + equiunet2020.py:60-61) or
  * EvoNorm3D-S0 (mode 1; networks/equiunet2021.py:48-52,95-105: x*sigmoid(x)/sqrt(var_unbiased+eps)*gamma+beta)
@@ -117,9 +151,10 @@ int b21_upsample2x(const void* x, int ldx, void* y, int ldy, int n, int d, int h
 int b21_upsample_f32(const float* x, float* y, int planes, int d, int h, int w, int s, void* stream);
 
 /* conv1x1 to k<=4 classes (outconv / out_conv / deep heads: equiunet2020.py:441-458, equiunet2021.py:271-280):
- * out (ncdhw fp32 [n][k][nvox]) = b + W (x * scale[n]) ; scale may be NULL. */
-int b21_head_conv(const void* x, int ldx, const float* scale, const float* w, const float* b, float* out, int n,
-                  long long nvox, int c, int k, void* stream);
+ * out (ncdhw fp32 [n][k][nvox]) = b + W (x * scale[n] + offset[n]); scale / offset ([n][ldso] fp32, the folded affine of
+ * the input: SE gate or EvoNorm (A, B)) may be NULL (= 1 / 0). */
+int b21_head_conv(const void* x, int ldx, const float* scale, const float* offset, int ldso, const float* w,
+                  const float* b, float* out, int n, long long nvox, int c, int k, void* stream);
 
 /* ------------------------------------------------------------------------- sliding window / TTA / labels
  * A TTA variant is (perm[3], flip[3]): augmented[a0,a1,a2] = volume[s0,s1,s2] with

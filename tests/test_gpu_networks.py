@@ -96,3 +96,30 @@ def test_state_dict_round_trip_and_repack():
     assert not torch.allclose(a, b)  # packed weights follow the parameters
     with pytest.raises(ValueError):
         net(torch.zeros((1, 4, 12, 16, 16), device=DEV))
+
+
+@pytest.mark.parametrize("width,shape,n", [(16, (16, 32, 48), 2), (48, (64, 64, 64), 1)])
+def test_v2_folded_evonorm_path_matches_explicit_path(width, shape, n):
+    """The folded-EvoNorm inference path (stored swish tensors, affine folded into the consumers: csrc/fold.cu) and
+    the explicit path (norm_apply passes) are two roundings of the same arithmetic: both must sit within the bf16
+    tolerance of the fp32 oracle and within 1.5e-2 rel-L2 of each other."""
+    from brats21_b200 import ops
+    from oracle import nets, synth
+    net, params = _build(2, width, 93)
+    x = torch.cat([synth.volume(seed=s, shape=shape) for s in range(n)]).to(DEV)
+    with torch.no_grad():
+        ref, ref_deeps = nets.equiunet_v2_forward(params, x)
+    assert ops.use_fold
+    net._ensure_packed()
+    assert net._fold_ok(*shape)
+    out_f, deeps_f = net(x)
+    ops.use_fold = False
+    try:
+        out_e, deeps_e = net(x)
+    finally:
+        ops.use_fold = True
+    _check(out_f, ref)
+    _check(out_e, ref)
+    for a, b in zip(deeps_f, ref_deeps):
+        _check(a, b)
+    assert ((out_f - out_e).norm() / out_e.norm()).item() <= 1.5e-2

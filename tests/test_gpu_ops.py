@@ -125,6 +125,94 @@ def test_conv3d_slide_matches_torch(cin, cout, shape):
         assert (_nc(dx) - ref_dx).abs().max().item() <= 2 ** -7 * ref_dx.abs().max().item()
 
 
+@pytest.mark.parametrize("cin,cout,k,shape", [
+    (48, 48, 3, (2, 6, 16, 16)), (96, 96, 3, (3, 7, 16, 24)), (16, 16, 3, (1, 2, 8, 8)), (64, 64, 3, (2, 5, 9, 11)),
+    (48, 24, 1, (3, 5, 6, 7)), (96, 48, 1, (2, 4, 4, 4)), (32, 32, 3, (4, 9, 10, 8))])
+def test_conv_fold_matches_explicit_affine(cin, cout, k, shape):
+    """Folded EvoNorm (csrc/fold.cu): conv with per-sample weights W*A and the border-class bias table on a stored
+    tensor S must equal the explicit formulation swish(conv(zero-padded A*S + B) + bias); statistics are those of the
+    pre-activation; channel sums are those of the stored outputs."""
+    from brats21_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin + 13 * cout + k)
+    n, d, h, w = shape
+    s_in = _cl(torch.randn((n, cin, d, h, w), device=DEV, generator=g))
+    a = torch.randn((n, cin), device=DEV, generator=g) * 0.5 + 1.0
+    a[:, ::5] *= -1.0
+    b = torch.randn((n, cin), device=DEV, generator=g) * 0.7
+    wt = torch.randn((cout, cin, k, k, k), device=DEV, generator=g) / (cin * k ** 3) ** 0.5
+    bias = torch.randn((cout,), device=DEV, generator=g)
+    pw = ops.PackedConv(wt, bias)
+    assert ops.fold_supported(pw)
+    ab = torch.stack([a, b])  # [2, n, cin]
+    st = ops.new_stats(n, DEV)
+    csum = torch.zeros((n, cout), device=DEV) if k == 3 else None
+    out = torch.empty((n, d, h, w, cout), device=DEV, dtype=torch.bfloat16)
+    ops.conv3d_fold(s_in, pw, out, st, ab=(ab[0], ab[1]), act=True, chan_sum=csum)
+    # explicit reference in fp32 with the SAME bf16-rounded folded weights the kernel uses
+    y_in = _nc(s_in) * 1.0
+    refs = []
+    for i in range(n):
+        wq = (wt * a[i].reshape(1, cin, 1, 1, 1)).to(torch.bfloat16).float()
+        z = F.conv3d(y_in[i:i + 1], wq, None, padding=k // 2)
+        ones = torch.ones((1, cin, d, h, w), device=DEV) * b[i].reshape(1, cin, 1, 1, 1)
+        z = z + F.conv3d(ones, wt, bias, padding=k // 2)  # response to the constant image B incl. the zero-padded border
+        refs.append(z)
+    z = torch.cat(refs)
+    ref = z * torch.sigmoid(z)
+    assert (_nc(out) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
+    r = z.reshape(n, 8, cout // 8, -1).double()
+    sm = st.sum(0)
+    assert torch.allclose(sm[..., 0], r.sum(dim=(2, 3)), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(sm[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-3, atol=5e-2)
+    if csum is not None:
+        assert torch.allclose(csum, _nc(out).sum(dim=(2, 3, 4)), rtol=1e-3, atol=5e-2)
+    # shared weights (no input affine), no activation == the plain conv
+    out2 = torch.empty_like(out)
+    ops.conv3d_fold(s_in, pw, out2, st, ab=None, act=False)
+    assert torch.equal(out2, ops.conv3d(s_in, pw))
+
+
+def test_evo_se_affine_and_affine_pool():
+    from brats21_b200 import ops
+    from oracle import nets
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n, c, d, h, w = 3, 32, 4, 6, 8
+    x = torch.randn((n, c, d, h, w), device=DEV, generator=g) * 1.3 + 0.2
+    gamma = 1 + 0.3 * torch.randn(c, device=DEV, generator=g)
+    gamma[3] = -0.8
+    beta = 0.2 * torch.randn(c, device=DEV, generator=g)
+    w1, b1 = torch.randn((c // 2, c), device=DEV, generator=g) * 0.3, torch.randn(c // 2, device=DEV, generator=g) * 0.1
+    w2, b2 = torch.randn((c, c // 2), device=DEV, generator=g) * 0.3, torch.randn(c, device=DEV, generator=g) * 0.1
+    st = torch.zeros((32, n, 8, 2), dtype=torch.float64, device=DEV)
+    r = x.reshape(n, 8, -1).double()
+    st[1, :, :, 0] = r.sum(-1)
+    st[5, :, :, 1] = (r * r).sum(-1)
+    sw = _cl(x * torch.sigmoid(x))           # what a folded conv epilogue stores
+    csum = _nc(sw).sum(dim=(2, 3, 4))
+    ab = torch.zeros((2, n, c + 8), device=DEV)
+    ops.evo_se_affine(st, gamma, beta, ab[0][:, 8:], ab[1][:, 8:], d * h * w, chan_sum=csum, se=(w1, b1, w2, b2))
+    y = nets.evonorm_s0(x, gamma, beta)
+    ref = nets.residual_se(y, w1, b1, w2, b2)
+    got = _nc(sw) * ab[0][:, 8:].reshape(n, c, 1, 1, 1) + ab[1][:, 8:].reshape(n, c, 1, 1, 1)
+    assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-3
+    assert (ab[:, :, :8] == 0).all()
+    # without SE
+    ab2 = torch.zeros((2, n, c), device=DEV)
+    ops.evo_se_affine(st, gamma, beta, ab2[0], ab2[1], d * h * w)
+    got2 = _nc(sw) * ab2[0].reshape(n, c, 1, 1, 1) + ab2[1].reshape(n, c, 1, 1, 1)
+    assert (got2 - y).abs().max().item() <= 2 ** -7 * y.abs().max().item() + 1e-3
+    # MaxAvgPool of the affine tensor (negative A -> min)
+    pooled = torch.zeros((n, d // 2, h // 2, w // 2, 2 * c), device=DEV, dtype=torch.bfloat16)
+    ops.affine_pool(sw, ab[0][:, 8:], ab[1][:, 8:], pooled, mode=2)
+    ref_pool = nets.max_avg_pool(got)
+    assert (_nc(pooled) - ref_pool).abs().max().item() <= 2 ** -7 * ref_pool.abs().max().item() + 1e-3
+    # head with scale + offset == head on the explicit tensor
+    wh, bh = torch.randn((3, c), device=DEV, generator=g) * 0.2, torch.randn(3, device=DEV, generator=g)
+    lo = ops.head_conv(sw, wh, bh, scale=ab[0][:, 8:], offset=ab[1][:, 8:])
+    ref_lo = F.conv3d(got, wh.reshape(3, c, 1, 1, 1), bh)
+    assert torch.allclose(lo, ref_lo, rtol=1e-4, atol=1e-4)
+
+
 def test_conv3d_argument_errors():
     from brats21_b200 import ops
     x = torch.zeros((1, 4, 4, 4, 12), device=DEV, dtype=torch.bfloat16)
