@@ -326,7 +326,10 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
           const float sv = valid ? val : 0.f;
           gs[c / GS] += sv;
           gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
-          if (p.ex.act) v[c] = swishf(val);
+        }
+        if (p.ex.act) {  // one branch around the whole unrolled loop: the 48 ex2/rcp chains interleave
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) v[c] = swishf(v[c]);
         }
         uint4 o[COUT / 8];
 #pragma unroll

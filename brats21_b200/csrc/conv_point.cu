@@ -207,7 +207,11 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float sv = valid ? val : 0.f;
         gs[c / GS] += sv;
         gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
-        v[c] = p.ex.act ? swishf(val) : val;
+        v[c] = val;
+      }
+      if (p.ex.act) {  // one branch around the whole unrolled loop: the ex2/rcp chains interleave
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) v[c] = swishf(v[c]);
       }
       if (valid) {
         __nv_bfloat16* yrow = p.y + (size_t(n) * p.nvox + r) * size_t(p.ldy);

@@ -377,7 +377,10 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           const float sv = valid ? val : 0.f;
           gs[c / GS] += sv;
           gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
-          if (p.ex.act) v[c] = swishf(val);
+        }
+        if (p.ex.act) {  // one branch around the whole unrolled loop: the ex2/rcp chains interleave
+#pragma unroll
+          for (int c = 0; c < NT; ++c) v[c] = swishf(v[c]);
         }
         uint32_t o[NT / 2];
 #pragma unroll

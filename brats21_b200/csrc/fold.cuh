@@ -12,7 +12,14 @@ struct FoldExtras {
 };
 
 __device__ __forceinline__ int border_class(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
-__device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)) on the MUFU pipe (ex2 + rcp, flush-to-zero: no range fix-up branches).
+// x -> -inf: ex2 -> +inf, rcp -> 0, result -0;  x -> +inf: ex2 -> 0, result x.
+__device__ __forceinline__ float swishf(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
 
 // Transposed warp reduction: every lane holds 32 values v[0..32); afterwards v[0] of lane l is the sum over all
 // lanes of their v[l] (31 shuffles instead of 32 x 5).
