@@ -318,25 +318,43 @@ def run_b200(args, wl, rank, local_rank, world):
         step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.conv_profile = []
     l0 = _lib.launch_count
     ms = timed(step_device, args.steps)
     launches = _lib.launch_count - l0
-    prof, ops.conv_profile = ops.conv_profile, None
     clocks = sampler.stop()
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # one more step, launched eagerly with a CUDA-event pair around every conv launch (the timed steps above replay
+    # the per-batch forward from a CUDA graph): live per-launch durations of the dominant kernel for the roofline
+    ops.conv_profile = []
+    step_device()
+    torch.cuda.synchronize()
+    prof, ops.conv_profile = ops.conv_profile, None
 
     # dominant kernel (conv implicit GEMM): algorithmic FLOPs / event-timed launch durations
     conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     conv_flops = sum(f for _, _, f, _ in prof)
     peak_tf, _, peak_kind = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv3d implicit GEMM (tcgen05), all launches of the timed region",
+    by_kind = {}
+    for a, b, fl, key in prof:
+        r = by_kind.setdefault(str(key[0]), [0, 0.0, 0.0])
+        r[0] += 1
+        r[1] += a.elapsed_time(b)
+        r[2] += fl
+    by_kind = {k: {"launches": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
+               for k, v in by_kind.items()}
+    roofline = {"bound": "tensor", "kernel": "conv3d implicit GEMM (tcgen05): all conv launches of one step "
+                "(march = plane-marching 48-ch layers, slide = sliding-window 96-ch layers, tap = generic, point = 1x1)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_kind": f"{peak_kind} bf16 (sustained)", "traffic": None,
+                "peak_kind": f"{peak_kind} bf16 (sustained)", "by_kernel": by_kind,
+                # DRAM bytes per launch of the dominant kernel (conv_march_kernel<48>, 48->48 at 4x128^3) from the
+                # ncu --set full capture profiles/r01c_conv_full.md; algorithmic bytes = 2 * 4*128^3 * 48 * 2 B = 1.61e9
+                "traffic": 1.577e9, "traffic_kernel": "conv_march_kernel<48> 48->48 @4x128^3",
+                "traffic_algorithmic": 1.611e9,
                 "launches": len(prof), "flops_per_launch": conv_flops / max(len(prof), 1),
-                "avg_launch_ms": conv_ms / max(len(prof), 1), "share_of_step": conv_ms / ms if ms > 0 else None}
+                "avg_launch_ms": conv_ms / max(len(prof), 1),
+                "share_of_step": conv_ms / (ms / args.steps) if ms > 0 else None}
 
     value = world * args.steps / (ms * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)

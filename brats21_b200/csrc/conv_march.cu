@@ -28,7 +28,7 @@
 
 namespace b21 {
 
-constexpr int kMThreads = 192;
+constexpr int kMThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 and 6..9: two epilogue groups (alternate planes)
 constexpr int kMTH = 16, kMTW = 8;                // in-plane output tile: M = 128 rows = 16 h x 8 w
 constexpr int kMHH = kMTH + 2, kMHW = kMTW + 2;   // halo plane 18 x 10
 constexpr int kMChunkData = kMHH * kMHW * 16;     // one 8-channel chunk of a halo plane (2880 B of TMA payload)
@@ -83,7 +83,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
   __shared__ __align__(8) uint64_t acce_bar[kMMaxRing];
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_stat[2][16];
+  __shared__ float s_stat[2][2][16];  // [epilogue group][double buffer][8 groups x (sum, sumsq)]
   __shared__ float s_bias[COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,7 +107,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
   }
-  if (threadIdx.x < 32) s_stat[threadIdx.x >> 4][threadIdx.x & 15] = 0.f;
+  if (threadIdx.x < 64) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
   for (int c = threadIdx.x; c < COUT; c += kMThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, 512);
@@ -258,19 +258,23 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
     }
   } else {
     // ------------------------------------------------------------------ epilogue (TMEM lane quadrant = warp % 4)
+    // Two groups of four warps drain alternate output planes (the epilogue, not the MMA, bounds the small-Cin layers).
     const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
     const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
     constexpr int GS = COUT / 8;  // channels per norm group
     // accumulators start at zero and are re-zeroed after every drain: the MMAs always accumulate
-    for (uint32_t c0 = 0; c0 < RING * COUT; c0 += 16) tmem_st16_zero(tlane + c0);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0)
-      for (uint32_t r = 0; r < RING; ++r) mbar_arrive_a(acce0 + 8u * r);
-    uint32_t r = 0, use_par = 0;
+    if (grp == 0) {
+      for (uint32_t c0 = 0; c0 < RING * COUT; c0 += 16) tmem_st16_zero(tlane + c0);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (uint32_t r = 0; r < RING; ++r) mbar_arrive_a(acce0 + 8u * r);
+    }
+    uint32_t r = 0, use_par = 0, plane_cnt = 0;
     int buf = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const MarchItem it = decode_item(p, item);
@@ -289,6 +293,11 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy);
       const size_t ystep = size_t(p.H) * p.W * p.ldy;
       for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
+        if (int((plane_cnt++) & 1u) != grp) {  // the other group's plane: only advance the ring cursor
+          use_par ^= 1u << r;
+          r = r + 1 == RING ? 0 : r + 1;
+          continue;
+        }
         mbar_wait_a(accf0 + 8u * r, (use_par >> r) & 1u);
         use_par ^= 1u << r;
         tc_fence_after();
@@ -373,14 +382,15 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
         for (int g = 0; g < 8; ++g) {
           const float a = warp_sum(gs[g]), b = warp_sum(gq[g]);
           if (lane == 0) {
-            atomicAdd(&s_stat[buf][g * 2], a);
-            atomicAdd(&s_stat[buf][g * 2 + 1], b);
+            atomicAdd(&s_stat[grp][buf][g * 2], a);
+            atomicAdd(&s_stat[grp][buf][g * 2 + 1], b);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-        if (warp == 2 && lane < 16) {
-          const float sv = s_stat[buf][lane];
-          s_stat[buf][lane] = 0.f;
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this epilogue group only
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (quad == 2 && lane < 16) {  // warp 2 / warp 6
+          const float sv = s_stat[grp][buf][lane];
+          s_stat[grp][buf][lane] = 0.f;
           if (sv != 0.f) {
             const int slot = item % B21_STAT_SLOTS;
             atomicAdd(p.stats + ((size_t(slot) * p.N + it.n) * 8) * 2 + lane, double(sv));

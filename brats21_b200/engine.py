@@ -126,7 +126,7 @@ def predict_volume(models: Sequence, image: torch.Tensor, tta_transforms: Option
                 ws = model._ws.setdefault(("full",) + tuple(adims), {})
                 x8 = model._buf(ws, "x8", (1,) + tuple(adims) + (8,))
                 ops.pack_windows(vol, x8, [(0, 0, 0)], perm=perm, flip=flip)
-                logits, _ = model.forward_packed(x8, want_deep=False)
+                logits = model.forward_infer(x8)
                 ops.tta_accumulate(logits[0], None, prob_sum, perm, flip)
             count += 1
     onehot, label = ops.labels_finalize(prob_sum, count, logit_thresh, image=vol[0] if remove_background else None)

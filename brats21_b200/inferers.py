@@ -141,7 +141,7 @@ def accumulate_windows(vol: torch.Tensor, vol_idx: int, net, plan: WindowPlan, s
         x8 = net._buf(ws, f"win{nb}", (nb, d, h, w, 8))
         shifted = [tuple(o - p for o, p in zip(org, plan.pad_before)) for org in group]
         ops.pack_windows(vol, x8, shifted, perm=perm, flip=flip, vol_index=[vol_idx] * nb)
-        logits, _ = net.forward_packed(x8, want_deep=False)
+        logits = net.forward_infer(x8)
         ops.blend_accumulate(logits, acc, plan.profiles, group)
 
 
@@ -227,6 +227,6 @@ def _fast_multi_volume(vol, net, plan, sw_batch_size, acc):
         x8 = net._buf(ws, f"win{len(idxs)}", (len(idxs), d, h, w, 8))
         shifted = [tuple(o - p for o, p in zip(org, plan.pad_before)) for org in group]
         ops.pack_windows(vol, x8, shifted, vol_index=vidx)
-        logits, _ = net.forward_packed(x8, want_deep=False)
+        logits = net.forward_infer(x8)
         for j, (o, b) in enumerate(zip(group, vidx)):
             ops.blend_accumulate(logits[j:j + 1], acc[b], plan.profiles, [o])

@@ -108,6 +108,7 @@ class _B21Net(nn.Module):
         self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self.skip_deep_heads_in_eval = False  # set by the inference wrappers (they discard the deep heads)
         self._gs = None  # flat gradient store of the training path (brats21_b200.autograd.GradStore)
+        self._graphs: Dict[Tuple, Tuple] = {}  # CUDA graphs of the inference forward, keyed by (input buffer, shape)
 
     # ---- training path (brats21_b200/autograd.py)
     def grad_store(self):
@@ -179,6 +180,31 @@ class _B21Net(nn.Module):
             nb = min(16, n - b0)
             ops.pack_windows(x, out[b0:b0 + nb], [(0, 0, 0)] * nb, vol_index=list(range(b0, b0 + nb)))
         return out
+
+    def forward_infer(self, x8: torch.Tensor) -> torch.Tensor:
+        """Logits of forward_packed(x8, want_deep=False).  The ~300 launches of one forward are captured once per
+        (input buffer, shape, weights) into a CUDA graph and replayed: the sliding-window loop re-uses the same window
+        buffer for every batch, so each further batch costs one graph launch instead of ~300 kernel launches."""
+        self._ensure_packed()
+        if not ops.use_graphs or ops.conv_profile is not None:
+            return self.forward_packed(x8, want_deep=False)[0]
+        key = (x8.data_ptr(), tuple(x8.shape), tuple(x8.stride()), ops.use_fold, ops.use_march, ops.use_slide,
+               ops.use_point)
+        if self._graphs.get("pack_key") != self._pack_key:  # weights changed: every captured graph is stale
+            self._graphs = {"pack_key": self._pack_key}
+        entry = self._graphs.get(key)
+        if entry is None:
+            self.forward_packed(x8, want_deep=False)  # warm-up: workspaces, lazily packed/folded weights, attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops._lib.launch_count
+            with torch.cuda.graph(graph):
+                out = self.forward_packed(x8, want_deep=False)[0]
+            entry = (graph, out, ops._lib.launch_count - l0)
+            self._graphs[key] = entry
+        entry[0].replay()
+        ops._lib.launch_count += entry[2]
+        return entry[1]
 
     def forward(self, x: torch.Tensor):
         train_fn = self._check_input(x)

@@ -72,13 +72,17 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+    kind = "tap"
     if use_point and pw.taps == 1 and pw.point_ok:
+        kind = "point"
         call("b21_conv1x1_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d * h * w, cin, pw.cout, stream_ptr())
     elif use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
+        kind = "march"
         call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())
     elif use_slide and dil == 1 and pw.w_slide is not None and h >= 8 and w >= 8:
+        kind = "slide"
         call("b21_conv3d_slide_fwd", ptr(x), _ld(x), ptr(pw.w_slide), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())
     else:
@@ -86,7 +90,7 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
              n, d, h, w, cin, pw.cout, pw.taps, dil, stream_ptr())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (cin, pw.cout, pw.taps, d)))
+        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (kind, cin, pw.cout, pw.taps, d)))
     return out
 
 
@@ -170,7 +174,8 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
              ptr(chan_sum), int(act), n, d, h, w, cin, pw.cout, stream_ptr())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (cin, pw.cout, pw.taps, d)))
+        kind = "point" if pw.taps == 1 else ("march" if pw.w_march is not None else "slide")
+        prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (kind, cin, pw.cout, pw.taps, d)))
     return out
 
 
@@ -192,6 +197,8 @@ use_march = True
 use_slide = True
 # folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations
 use_fold = True
+# replay the inference forward of a window batch from a CUDA graph (networks._B21Net.forward_infer)
+use_graphs = True
 # persistent 1x1 kernel (conv_point.cu) for the shapes it supports
 use_point = True
 
