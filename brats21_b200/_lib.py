@@ -41,9 +41,9 @@ _SIGNATURES = {
     "b21_evo_se_affine": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _f, _vp],
     "b21_border_weight_sums": [_vp, _vp, _i, _i, _i, _vp],
     "b21_bias_table": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
-    "b21_pack_conv_weight_fold": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
-    "b21_pack_conv_weight_march_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp],
-    "b21_pack_conv_weight_slide_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp],
+    "b21_pack_conv_weight_fold": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b21_pack_conv_weight_march_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b21_pack_conv_weight_slide_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b21_conv3d_march_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv3d_slide_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv1x1_fwd_fold": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp],

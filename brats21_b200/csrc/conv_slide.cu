@@ -444,13 +444,19 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
 // scale != NULL: per-sample copies (blockIdx.y = sample) with the input channels multiplied by scale[sample][ci].
 __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
                                          int cin_o, int rows, int kc, int nt, int transpose_flip,
-                                         const float* __restrict__ scale = nullptr, int ldscale = 0) {
+                                         const float* __restrict__ scale = nullptr, int ldscale = 0,
+                                         int pack_blocks = 0, BiasTableArgs tab = BiasTableArgs()) {
+  if (pack_blocks > 0 && int(blockIdx.x) >= pack_blocks) {  // appended blocks: one bias-table row each
+    bias_table_block(tab, blockIdx.x - pack_blocks, blockIdx.y);
+    return;
+  }
   const int ng = nt / 8;
   const int ntiles = rows / nt;
   const size_t total = size_t(ntiles) * 27 * kc * ng * 64;
+  const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride) {
     const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
     size_t t = i >> 6;
     const int g = int(t % ng); t /= ng;
@@ -560,15 +566,18 @@ extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout
 }
 
 extern "C" int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int cout, int cin, const float* scale,
-                                               int ldscale, int nsamples, void* stream) {
+                                               int ldscale, int nsamples, const float* ws, const float* bias,
+                                               const float* b_in, float* table, void* stream) {
   B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_slide_fold: bad args");
+  B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_slide_fold: the bias table needs ws and B");
   SlideCfg c;
   B21_CHECK_ARG(slide_config(cin, cout, &c), "pack_conv_weight_slide_fold: (cin %d, cout %d) unsupported", cin, cout);
   const size_t total = size_t(27) * c.kc * cout * 8;
   const int threads = 256;
   const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
-  pack_slide_weight_kernel<<<dim3(bx, nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale);
+  BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, 27};
+  pack_slide_weight_kernel<<<dim3(bx + (table ? 27 : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale, bx, tab);
   B21_LAUNCH_CHECK("pack_slide_weight_kernel(fold)");
   return B21_OK;
 }

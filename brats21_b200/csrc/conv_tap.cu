@@ -14,6 +14,7 @@
 // networks/equiunet2020.py:19-41, networks/equiunet2021.py:165-172,192-222.  The plane-marching kernel in
 // conv_march.cu is the faster specialisation for the dil=1, small-channel layers that hold most of the FLOPs.
 #include "ptx.cuh"
+#include "fold.cuh"
 #include "host_common.h"
 
 namespace b21 {
@@ -200,11 +201,17 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // scale != NULL: per-sample copies (blockIdx.y = sample) with the input channels multiplied by scale[sample][ci].
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
                                         int cin, int rows_padded, int inner_padded, int T, int transpose_flip,
-                                        const float* __restrict__ scale = nullptr, int ldscale = 0) {
+                                        const float* __restrict__ scale = nullptr, int ldscale = 0,
+                                        int pack_blocks = 0, BiasTableArgs tab = BiasTableArgs()) {
+  if (pack_blocks > 0 && int(blockIdx.x) >= pack_blocks) {  // appended blocks: one bias-table row each
+    bias_table_block(tab, blockIdx.x - pack_blocks, blockIdx.y);
+    return;
+  }
   const size_t total = size_t(T) * rows_padded * inner_padded;
+  const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride) {
     const int ki = int(i % inner_padded);
     const int r = int((i / inner_padded) % rows_padded);
     const int tap = int(i / (size_t(inner_padded) * rows_padded));
@@ -260,8 +267,10 @@ extern "C" int b21_pack_conv_weight(const float* w, void* packed, int cout, int 
 
 // Per-sample folded packing (k = 1 or 3): packed[s] = pack(w * scale[s][ci]), taps*cout_padded*cin_padded bf16 apart.
 extern "C" int b21_pack_conv_weight_fold(const float* w, void* packed, int cout, int cin, int cin_padded, int k,
-                                         const float* scale, int ldscale, int nsamples, void* stream) {
+                                         const float* scale, int ldscale, int nsamples, const float* ws,
+                                         const float* bias, const float* b_in, float* table, void* stream) {
   B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_fold: bad args");
+  B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_fold: the bias table needs ws and B");
   B21_CHECK_ARG(k == 1 || k == 3, "pack_conv_weight_fold: k must be 1 or 3 (got %d)", k);
   B21_CHECK_ARG(cin_padded >= cin && cin_padded % 8 == 0, "pack_conv_weight_fold: bad inner padding");
   const int T = k * k * k;
@@ -269,8 +278,10 @@ extern "C" int b21_pack_conv_weight_fold(const float* w, void* packed, int cout,
   const size_t total = size_t(T) * rows_padded * cin_padded;
   const int threads = 256;
   const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
-  pack_conv_weight_kernel<<<dim3(bx, nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, 0, scale, ldscale);
+  const int ncls = T == 27 ? 27 : 1;
+  BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, ncls};
+  pack_conv_weight_kernel<<<dim3(bx + (table ? ncls : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, 0, scale, ldscale, bx, tab);
   B21_LAUNCH_CHECK("pack_conv_weight_kernel(fold)");
   return B21_OK;
 }

@@ -276,6 +276,92 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
   }
 }
 
+// Faster x2 variant: one thread per (INPUT voxel, 8-channel chunk) produces the 2x2x2 output block.  The two outputs
+// of an axis interpolate between the inputs {i-1, i, i+1} only (align_corners=True: src = o (I-1)/(2I-1)), so the
+// block needs 2 x 9 loads per output plane instead of 8 per output voxel, and the interpolation is done separably
+// (d, then h, then w).  Weights come from the same lerp_setup as the reference formulation.
+__device__ __forceinline__ void axis_slots(int i, int I, float w0[3], float w1[3]) {
+  // weights of outputs 2i (w0) and 2i+1 (w1) over the input slots (i-1, i, i+1)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w0[k] = w1[k] = 0.f;
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    int i0, i1;
+    float l;
+    lerp_setup(2 * i + par, I, 2 * I, i0, i1, l);
+    float* wv = par ? w1 : w0;
+    const int s0 = i0 - i + 1, s1 = i1 - i + 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wv[k] += (s0 == k ? 1.f - l : 0.f) + (s1 == k ? l : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) upsample2x_block_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                               __nv_bfloat16* __restrict__ y, int ldy, int N, int D,
+                                                               int H, int W, int C) {
+  const int chunks = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * D * 2 * H * W * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ck = int(i % chunks);
+    long long v = i / chunks;
+    const int iw = int(v % W); v /= W;
+    const int ih = int(v % H); v /= H;
+    const int od = int(v & 1); v >>= 1;  // one thread per output d plane of the block (register pressure)
+    const int id = int(v % D);
+    const int n = int(v / D);
+    float wd[2][3], wh[2][3], ww[2][3];
+    axis_slots(id, D, wd[0], wd[1]);
+    axis_slots(ih, H, wh[0], wh[1]);
+    axis_slots(iw, W, ww[0], ww[1]);
+    int hs[3], wsl[3], ds[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ds[k] = min(max(id + k - 1, 0), D - 1);
+      hs[k] = min(max(ih + k - 1, 0), H - 1);
+      wsl[k] = min(max(iw + k - 1, 0), W - 1);
+    }
+    const __nv_bfloat16* xn = x + size_t(n) * D * H * W * ldx + ck * 8;
+    {
+      // the two d planes this output plane interpolates: slots (0,1) for od = 0, (1,2) for od = 1; a weight that
+      // rounding put on the third slot (at most 1 ulp of the coordinate) is added to its neighbour
+      const int pa = od == 0 ? 0 : 1, pb = pa + 1;
+      const float wa = wd[od][pa] + (od == 0 ? 0.f : wd[od][0]), wb = wd[od][pb] + (od == 0 ? wd[od][2] : 0.f);
+      float t[3][3][8];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const size_t off = (size_t(hs[b]) * W + wsl[c]) * ldx;
+          float fa[8], fb[8];
+          unpack8(ldg16(xn + size_t(ds[pa]) * H * W * ldx + off), fa);
+          unpack8(ldg16(xn + size_t(ds[pb]) * H * W * ldx + off), fb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[b][c][j] = fmaf(wb, fb[j], wa * fa[j]);
+        }
+      }
+#pragma unroll
+      for (int oh = 0; oh < 2; ++oh) {
+        float u[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            u[c][j] = fmaf(wh[oh][2], t[2][c][j], fmaf(wh[oh][1], t[1][c][j], wh[oh][0] * t[0][c][j]));
+#pragma unroll
+        for (int ow = 0; ow < 2; ++ow) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(ww[ow][2], u[2][j], fmaf(ww[ow][1], u[1][j], ww[ow][0] * u[0][j]));
+          const size_t ov = ((size_t(n) * 2 * D + (2 * id + od)) * Ho + (2 * ih + oh)) * Wo + (2 * iw + ow);
+          *reinterpret_cast<uint4*>(y + ov * ldy + ck * 8) = pack8(o);
+        }
+      }
+    }
+  }
+}
+
 // trilinear xS on NCDHW fp32 planes (deep-supervision heads): one thread per output element
 __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            int planes, int D, int H, int W, int S) {
@@ -414,6 +500,15 @@ extern "C" int b21_scale_pool(const void* x, int ldx, const float* scale, void* 
 extern "C" int b21_upsample2x(const void* x, int ldx, void* y, int ldy, int n, int d, int h, int w, int c,
                               void* stream) {
   B21_CHECK_ARG(x && y && c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x: bad args");
+  if (d >= 2 && h >= 2 && w >= 2) {
+    const long long items = (long long)n * d * 2 * h * w * (c / 8);
+    long long blocks = (items + 127) / 128;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    upsample2x_block_kernel<<<int(blocks), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, n, d, h, w, c);
+    B21_LAUNCH_CHECK("upsample2x_block_kernel");
+    return B21_OK;
+  }
   const long long items = (long long)n * d * h * w * 8 * (c / 8);
   upsample2x_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, n, d, h, w, c);
   B21_LAUNCH_CHECK("upsample2x_kernel");

@@ -38,20 +38,32 @@ __global__ void evo_se_affine_kernel(const double* __restrict__ stats, const flo
                                      const float* __restrict__ w2, const float* __restrict__ b2,
                                      float* __restrict__ A, float* __restrict__ B, int ldab, int N, int C, int Hd,
                                      long long nvox, float eps) {
-  extern __shared__ float sm[];  // a[C], m[C], hid[Hd]
+  extern __shared__ float sm[];  // a[C], m[C], hid[Hd], w1[Hd*C], w2[C*Hd]
+  __shared__ double sred[16];    // per (group, {sum, sumsq}) totals over the contention-spreading slots
   float* sa = sm;
   float* m = sm + C;
   float* hid = sm + 2 * C;
+  float* sw1 = hid + Hd;
+  float* sw2 = sw1 + Hd * C;
   const int n = blockIdx.x;
   const int gsz = C / 8;
+  if (chan_sum) {  // the MLP weights are cold in L2 by now: fetch them with all loads in flight, under the stats reduction
+    for (int i = threadIdx.x; i < Hd * C; i += blockDim.x) {
+      sw1[i] = __ldg(w1 + i);
+      sw2[i] = __ldg(w2 + i);
+    }
+  }
+  if (threadIdx.x < 16) sred[threadIdx.x] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B21_STAT_SLOTS * 16; i += blockDim.x) {  // all slot loads in flight at once
+    double v = stats[(size_t(i >> 4) * N + n) * 16 + (i & 15)];
+    v += __shfl_xor_sync(0xffffffffu, v, 16);  // lanes l and l + 16 hold the same (group, k)
+    if ((threadIdx.x & 31) < 16) atomicAdd(&sred[i & 15], v);
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / gsz;
-    double s = 0.0, q = 0.0;
-    for (int slot = 0; slot < B21_STAT_SLOTS; ++slot) {
-      const double* p = stats + ((size_t(slot) * N + n) * 8 + g) * 2;
-      s += p[0];
-      q += p[1];
-    }
+    const double s = sred[g * 2], q = sred[g * 2 + 1];
     const double cnt = double(nvox) * gsz;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -71,14 +83,14 @@ __global__ void evo_se_affine_kernel(const double* __restrict__ stats, const flo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int j = warp; j < Hd; j += nw) {
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += w1[size_t(j) * C + c] * m[c];
+    for (int c = lane; c < C; c += 32) s += sw1[j * C + c] * m[c];
     s = warp_sum(s);
     if (lane == 0) hid[j] = fmaxf(s + b1[j], 0.f);
   }
   __syncthreads();
   for (int c = warp; c < C; c += nw) {
     float s = 0.f;
-    for (int j = lane; j < Hd; j += 32) s += w2[size_t(c) * Hd + j] * hid[j];
+    for (int j = lane; j < Hd; j += 32) s += sw2[c * Hd + j] * hid[j];
     s = warp_sum(s);
     if (lane == 0) {
       const float gate = 1.f + 1.f / (1.f + expf(-(s + b2[c])));
@@ -193,7 +205,14 @@ extern "C" int b21_evo_se_affine(const double* stats, const float* gamma, const 
   B21_CHECK_ARG(stats && gamma && beta && a_out && b_out, "evo_se_affine: null pointer");
   B21_CHECK_ARG(n > 0 && c > 0 && c % 8 == 0 && ldab >= c && nvox > 0, "evo_se_affine: bad sizes");
   if (chan_sum) B21_CHECK_ARG(w1 && b1 && w2 && b2 && hidden > 0, "evo_se_affine: SE gate needs its MLP");
-  evo_se_affine_kernel<<<n, 256, sizeof(float) * (2 * c + (chan_sum ? hidden : 0)), (cudaStream_t)stream>>>(
+  const size_t smem = sizeof(float) * (2 * c + (chan_sum ? hidden + 2 * size_t(hidden) * c : 0));
+  B21_CHECK_ARG(smem <= 200 * 1024, "evo_se_affine: SE MLP of %d channels does not fit in shared memory", c);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B21_CUDA(cudaFuncSetAttribute(evo_se_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  evo_se_affine_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(
       stats, gamma, beta, chan_sum, w1, b1, w2, b2, a_out, b_out, ldab, n, c, hidden, nvox, eps);
   B21_LAUNCH_CHECK("evo_se_affine_kernel");
   return B21_OK;

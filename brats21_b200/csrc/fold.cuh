@@ -37,4 +37,36 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
   return v[0];
 }
 
+// Bias-table rows computed by the extra blocks appended to the per-sample weight packing kernels (one launch per
+// consumer conv): T[n][cls][co] = bias[co] + sum_ci ws[cls][ci][co] * B[n][ci].
+struct BiasTableArgs {
+  const float* ws;     // [ncls][cin][cout] border-class tap sums of the fp32 weight (b21_border_weight_sums)
+  const float* bias;   // [cout] or NULL
+  const float* b_in;   // B[n][ci], row stride ld
+  float* table;        // [n][ncls][cout]
+  int ld, cout, cin, ncls;
+};
+__device__ __forceinline__ void bias_table_block(const BiasTableArgs& t, int cls, int n) {
+  // ws is cold in L2 by the time the next forward needs it: issue the loads of a row block up front (independent of
+  // the accumulation chain) instead of one dependent load per multiply-add
+  const float* bp = t.b_in + size_t(n) * t.ld;
+  for (int co = threadIdx.x; co < t.cout; co += blockDim.x) {
+    const float* wp = t.ws + size_t(cls) * t.cin * t.cout + co;
+    float s = t.bias ? t.bias[co] : 0.f;
+    int ci = 0;
+    for (; ci + 16 <= t.cin; ci += 16) {
+      float wv[16], bv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        wv[k] = __ldg(wp + size_t(ci + k) * t.cout);
+        bv[k] = __ldg(bp + ci + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s = fmaf(wv[k], bv[k], s);
+    }
+    for (; ci < t.cin; ++ci) s = fmaf(__ldg(wp + size_t(ci) * t.cout), __ldg(bp + ci), s);
+    t.table[(size_t(n) * t.ncls + cls) * t.cout + co] = s;
+  }
+}
+
 }  // namespace b21

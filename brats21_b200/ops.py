@@ -131,14 +131,13 @@ def _fold_prepare(pw: "PackedConv", a_in, b_in):
                   torch.empty((n, ncls, pw.cout), dtype=torch.float32, device=dev))
     packed, table = f[key]
     ld = a_in.stride(0)
+    tail = (ptr(f["ws"]), ptr(pw.bias), ptr(b_in), ptr(table), stream_ptr())  # bias table in the same launch
     if pw.taps == 1:
-        call("b21_pack_conv_weight_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, pw.cin, 1, ptr(a_in), ld, n,
-             stream_ptr())
+        call("b21_pack_conv_weight_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, pw.cin, 1, ptr(a_in), ld, n, *tail)
     elif pw.w_march is not None:
-        call("b21_pack_conv_weight_march_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, stream_ptr())
+        call("b21_pack_conv_weight_march_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, *tail)
     else:
-        call("b21_pack_conv_weight_slide_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, stream_ptr())
-    call("b21_bias_table", ptr(f["ws"]), ptr(pw.bias), ptr(b_in), ld, ptr(table), n, pw.cout, cin, ncls, stream_ptr())
+        call("b21_pack_conv_weight_slide_fold", ptr(pw.w32), ptr(packed), pw.cout, cin, ptr(a_in), ld, n, *tail)
     return packed, packed.stride(0) * 2, table
 
 

@@ -103,12 +103,17 @@ int b21_evo_se_affine(const double* stats, const float* gamma, const float* beta
 int b21_border_weight_sums(const float* w, float* ws, int cout, int cin, int taps, void* stream);
 int b21_bias_table(const float* ws, const float* bias, const float* b_in, int ldab, float* table, int n, int cout,
                    int cin, int ncls, void* stream);
+/* The per-sample packing kernels also emit the bias table in the same launch when `table` != NULL
+ * (ws / bias / b_in as for b21_bias_table; B rows share `ldscale`). */
 int b21_pack_conv_weight_fold(const float* w, void* packed, int cout, int cin, int cin_padded, int k,
-                              const float* scale, int ldscale, int nsamples, void* stream);
+                              const float* scale, int ldscale, int nsamples, const float* ws, const float* bias,
+                              const float* b_in, float* table, void* stream);
 int b21_pack_conv_weight_march_fold(const float* w, void* packed, int cout, int cin, const float* scale, int ldscale,
-                                    int nsamples, void* stream);
+                                    int nsamples, const float* ws, const float* bias, const float* b_in, float* table,
+                                    void* stream);
 int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int cout, int cin, const float* scale, int ldscale,
-                                    int nsamples, void* stream);
+                                    int nsamples, const float* ws, const float* bias, const float* b_in, float* table,
+                                    void* stream);
 int b21_conv3d_march_fwd_fold(const void* x, int ldx, const void* w_march, long long wstride_n, const float* bias,
                               const float* bias_table, void* y, int ldy, double* stats, float* chan_sum, int act,
                               int n, int d, int h, int w, int cin, int cout, void* stream);
