@@ -53,6 +53,8 @@ _SIGNATURES = {
     "b21_tta_accumulate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp],
     "b21_labels_finalize": [_vp, _f, _f, _vp, _i, _vp, _vp, _i64, _i, _vp],
     "b21_conv3d_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv_wgrad_march_supported": [_i, _i],
+    "b21_conv3d_wgrad_march": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_norm_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                      _vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _f, _vp],
     "b21_pool_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -117,7 +119,7 @@ def stream_ptr():
 
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
-             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
+             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
 launch_count = 0
 
 

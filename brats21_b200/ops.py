@@ -198,6 +198,8 @@ use_slide = True
 use_fold = True
 # replay the inference forward of a window batch from a CUDA graph (networks._B21Net.forward_infer)
 use_graphs = True
+# plane-marching weight gradient (conv_wgrad_march.cu) for the k = 3 layers with cin <= 96
+use_wgrad_march = True
 # persistent 1x1 kernel (conv_point.cu) for the shapes it supports
 use_point = True
 
@@ -328,6 +330,19 @@ def conv3d_wgrad(x, dz, dw, dil: int = 1):
     cout = dz.shape[-1]
     k = dw.shape[2]
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[0] == cout and dw.shape[1] <= cin
+    if use_wgrad_march and k == 3 and dil == 1 and h >= 8 and w >= 8 and \
+            _lib.load().b21_conv_wgrad_march_supported(cin, cout):
+        prof = conv_profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        call("b21_conv3d_wgrad_march", ptr(x), _ld(x), ptr(dz), _ld(dz), ptr(dw), n, d, h, w, cin, dw.shape[1], cout,
+             stream_ptr())
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * n * d * h * w * dw.shape[1] * cout * 27, ("wgrad_march", cin, cout, 27, d)))
+        return dw
     if dw.shape[1] != cin:  # input channels were zero-padded for the forward pass (first layer): use a padded scratch
         tmp = torch.zeros((cout, cin) + tuple(dw.shape[2:]), dtype=torch.float32, device=dw.device)
         call("b21_conv3d_wgrad", ptr(x), _ld(x), ptr(dz), _ld(dz), ptr(tmp), n, d, h, w, cin, cout, k ** 3, dil,

@@ -202,6 +202,14 @@ int b21_labels_finalize(const float* prob_sum, float count, float thresh, const 
 int b21_conv3d_wgrad(const void* x, int ldx, const void* dz, int lddz, float* dw, int n, int d, int h, int w, int cin,
                      int cout, int taps, int dil, void* stream);
 
+/* Plane-marching variant of b21_conv3d_wgrad for k = 3, dilation 1, cin <= 96, cout <= 128, h, w >= 8
+ * (b21_conv_wgrad_march_supported): x halo planes and dz planes are read once into shared memory, taps are descriptor
+ * start addresses, the three kd taps are folded into the MMA N dimension.  `cin` is the channel count of x (multiple
+ * of 8, may include zero padding), `cin_true` <= cin the input-channel count of dw [cout][cin_true][27]. */
+int b21_conv_wgrad_march_supported(int cin, int cout);
+int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, int lddz, float* dw, int n, int d, int h, int w,
+                           int cin, int cin_true, int cout, void* stream);
+
 /* Backward of b21_norm_apply (mode 0 GroupNorm(8)+ReLU, mode 1 EvoNorm3D-S0) from the pre-norm tensor z and the
  * forward statistics; dy is the gradient of the layer output.  With se_w1 != NULL the layer output was additionally
  * multiplied by the MONAI ResidualSELayer gate (b21_se_gate: se_scale, from the channel means se_mean) and dy is the

@@ -211,6 +211,42 @@ def test_conv_wgrad_matches_autograd(cin, cout, k, dil, shape):
     assert _rel(dw2, wt.grad) < 1e-3
 
 
+@pytest.mark.parametrize("cin,cin_true,cout,shape", [
+    (48, 48, 48, (1, 16, 16, 16)), (48, 48, 48, (2, 7, 20, 12)), (96, 96, 96, (1, 9, 16, 16)), (8, 4, 48, (1, 6, 16, 8)),
+    (16, 16, 16, (2, 5, 9, 11)), (32, 32, 64, (1, 8, 8, 8)), (96, 96, 48, (1, 5, 8, 24)), (64, 64, 128, (1, 4, 8, 8)),
+    (48, 48, 48, (1, 40, 24, 24))])
+def test_conv_wgrad_march_matches_autograd(cin, cin_true, cout, shape):
+    """conv_wgrad_march.cu (x / dz planes resident in shared memory, MN-major SWIZZLE_NONE operands, kd folded into N)
+    against torch autograd and against the generic wgrad kernel; channel-slice operands, ragged tiles, several d
+    segments, zero-padded input channels (first layer)."""
+    from brats21_b200 import _lib, ops
+    assert _lib.load().b21_conv_wgrad_march_supported(cin, cout)
+    g = torch.Generator(device=DEV).manual_seed(cin + 7 * cout)
+    n, d, h, w = shape
+    x = torch.randn((n, cin, d, h, w), device=DEV, generator=g)
+    x[:, cin_true:] = 0
+    big_x = torch.full((n, d, h, w, cin + 16), 3.0, dtype=torch.bfloat16, device=DEV)
+    big_x[..., 8:8 + cin] = _cl(x)
+    xb = big_x[..., 8:8 + cin]
+    big_z = torch.full((n, d, h, w, cout + 8), -2.0, dtype=torch.bfloat16, device=DEV)
+    big_z[..., :cout] = _cl(torch.randn((n, cout, d, h, w), device=DEV, generator=g))
+    dzb = big_z[..., :cout]
+    wt = torch.zeros((cout, cin_true, 3, 3, 3), device=DEV, requires_grad=True)
+    y = F.conv3d(_nc(xb)[:, :cin_true], wt, None, padding=1)
+    y.backward(_nc(dzb))
+    dw = torch.full((cout, cin_true, 3, 3, 3), 0.5, device=DEV)  # accumulates onto what is there
+    assert ops.use_wgrad_march
+    ops.conv3d_wgrad(xb, dzb, dw)
+    assert _rel(dw - 0.5, wt.grad) < 1e-3
+    ops.use_wgrad_march = False
+    try:
+        dw2 = torch.zeros_like(dw)
+        ops.conv3d_wgrad(xb, dzb, dw2)
+    finally:
+        ops.use_wgrad_march = True
+    assert _rel(dw - 0.5, dw2) < 1e-3
+
+
 def test_conv_dgrad_is_conv_with_flipped_weights():
     from brats21_b200 import ops
     g = torch.Generator(device=DEV).manual_seed(11)
