@@ -20,6 +20,7 @@
 // Backward of networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201 (learning/engine.py:117 backward()).
 #include "ptx.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace b21 {
 
@@ -39,6 +40,7 @@ struct WgMarchParams {
   int G2, groups, fold;          // (kh, kw) taps per CTA, number of tap groups, max planes per MMA (N <= 256)
   int items_per_split;
   int xslots, zstages;
+  int variant;  // debug (B21_WGM_VARIANT): bit0 skip the final atomics, bit1 one K-step per tap
 };
 
 struct WgItem {
@@ -176,6 +178,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
               const uint32_t xa = xs0 + uint32_t((t9 / 3) * kWMHW + (t9 % 3));
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)  // K = 16 voxels = two h rows of the tile
+                if (ks == 0 || !(p.variant & 2))
                 umma_bf16(dcol, (uint64_t(z_hi) << 32) | (za + ks * 16u), (uint64_t(x_hi) << 32) | (xa + ks * 20u), idesc, 1u);
             }
             j += len;
@@ -215,7 +218,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             float v[16];
             tmem_ld16(tlane + uint32_t((t * 3 + kd) * p.ncolx + c0), v);
             tmem_ld_wait();
-            if (co < p.Cout) {
+            if (co < p.Cout && !(p.variant & 1)) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int ci = c0 + i;
@@ -287,6 +290,12 @@ extern "C" int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, in
   p.xslots = c.xslots; p.zstages = c.zstages;
   p.tilesH = (h + kWMTH - 1) / kWMTH;
   p.tilesW = (w + kWMTW - 1) / kWMTW;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("B21_WGM_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  p.variant = variant;
   // split-K: groups x splits CTAs ~ 1 per SM; d segments so that every split gets several items
   const int sms = num_sms();
   int splits = sms / p.groups;
