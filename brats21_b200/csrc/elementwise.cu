@@ -12,6 +12,7 @@
 //   head_conv    1x1 conv C -> K<=4 logits, NCDHW fp32 out                         (equiunet2020.py:441, 2021.py:271)
 //   upsample_f32 trilinear xS (align_corners) on NCDHW fp32 (deep-supervision heads, equiunet2021.py:274-280)
 #include "ptx.cuh"
+#include "fold.cuh"
 #include "host_common.h"
 
 namespace b21 {
@@ -82,12 +83,15 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
   const __nv_bfloat16* xn = x + size_t(n) * nvox * ldx;
   __nv_bfloat16* yn = y + size_t(n) * nvox * ldy;
   constexpr int U = 4;
-  for (; i < total; i += T * U) {
+  // T is a multiple of `chunks`: the voxel index advances by T / chunks per step (no 64-bit division in the loop)
+  const long long vstep = T / chunks;
+  long long v0 = i / chunks;
+  for (; i < total; i += T * U, v0 += vstep * U) {
     uint4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long iu = i + u * T;
-      if (iu < total) v[u] = *reinterpret_cast<const uint4*>(xn + (iu / chunks) * ldx + ck * 8);
+      if (iu < total) v[u] = *reinterpret_cast<const uint4*>(xn + (v0 + u * vstep) * ldx + ck * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
           if (MODE == 0) {
             r = fmaxf(fmaf(f[j], a[j], b[j]), 0.f);
           } else {
-            const float sw = __fdividef(f[j], 1.f + __expf(-f[j]));  // x * sigmoid(x)
+            const float sw = swishf(f[j]);  // x * sigmoid(x)
             r = fmaf(sw, a[j], b[j]);
           }
           f[j] = r;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += g[j];
         }
-        *reinterpret_cast<uint4*>(yn + (iu / chunks) * ldy + ck * 8) = o;
+        *reinterpret_cast<uint4*>(yn + (v0 + u * vstep) * ldy + ck * 8) = o;
       }
     }
   }
@@ -301,16 +305,16 @@ __global__ void __launch_bounds__(128, 4) upsample2x_block_kernel(const __nv_bfl
                                                                int H, int W, int C) {
   const int chunks = C >> 3;
   const int Ho = 2 * H, Wo = 2 * W;
-  const long long total = (long long)N * D * 2 * H * W * chunks;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ck = int(i % chunks);
-    long long v = i / chunks;
-    const int iw = int(v % W); v /= W;
-    const int ih = int(v % H); v /= H;
-    const int od = int(v & 1); v >>= 1;  // one thread per output d plane of the block (register pressure)
-    const int id = int(v % D);
-    const int n = int(v / D);
+  // grid: x over (iw, chunk), y = ih, z = (n, id, od): no 64-bit divisions in the index math
+  {
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tx >= W * chunks) return;
+    const int ck = tx % chunks;
+    const int iw = tx / chunks;
+    const int ih = blockIdx.y;
+    const int od = blockIdx.z & 1;  // one thread per output d plane of the block (register pressure)
+    const int id = (blockIdx.z >> 1) % D;
+    const int n = (blockIdx.z >> 1) / D;
     float wd[2][3], wh[2][3], ww[2][3];
     axis_slots(id, D, wd[0], wd[1]);
     axis_slots(ih, H, wh[0], wh[1]);
@@ -326,8 +330,11 @@ __global__ void __launch_bounds__(128, 4) upsample2x_block_kernel(const __nv_bfl
     {
       // the two d planes this output plane interpolates: slots (0,1) for od = 0, (1,2) for od = 1; a weight that
       // rounding put on the third slot (at most 1 ulp of the coordinate) is added to its neighbour
-      const int pa = od == 0 ? 0 : 1, pb = pa + 1;
-      const float wa = wd[od][pa] + (od == 0 ? 0.f : wd[od][0]), wb = wd[od][pb] + (od == 0 ? wd[od][2] : 0.f);
+      float wdo[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wdo[k] = od ? wd[1][k] : wd[0][k];  // selects, not dynamic register indexing
+      const int dsa = od == 0 ? ds[0] : ds[1], dsb = od == 0 ? ds[1] : ds[2];
+      const float wa = od == 0 ? wdo[0] : wdo[1] + wdo[0], wb = od == 0 ? wdo[1] + wdo[2] : wdo[2];
       float t[3][3][8];
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
@@ -335,8 +342,8 @@ __global__ void __launch_bounds__(128, 4) upsample2x_block_kernel(const __nv_bfl
         for (int c = 0; c < 3; ++c) {
           const size_t off = (size_t(hs[b]) * W + wsl[c]) * ldx;
           float fa[8], fb[8];
-          unpack8(ldg16(xn + size_t(ds[pa]) * H * W * ldx + off), fa);
-          unpack8(ldg16(xn + size_t(ds[pb]) * H * W * ldx + off), fb);
+          unpack8(ldg16(xn + size_t(dsa) * H * W * ldx + off), fa);
+          unpack8(ldg16(xn + size_t(dsb) * H * W * ldx + off), fb);
 #pragma unroll
           for (int j = 0; j < 8; ++j) t[b][c][j] = fmaf(wb, fb[j], wa * fa[j]);
         }
@@ -501,11 +508,9 @@ extern "C" int b21_upsample2x(const void* x, int ldx, void* y, int ldy, int n, i
                               void* stream) {
   B21_CHECK_ARG(x && y && c % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x: bad args");
   if (d >= 2 && h >= 2 && w >= 2) {
-    const long long items = (long long)n * d * 2 * h * w * (c / 8);
-    long long blocks = (items + 127) / 128;
-    const long long cap = (long long)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    upsample2x_block_kernel<<<int(blocks), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, n, d, h, w, c);
+    B21_CHECK_ARG(h <= 65535 && (long long)n * d * 2 <= 65535, "upsample2x: volume too large for the launch grid");
+    dim3 grid((w * (c / 8) + 127) / 128, h, n * d * 2);
+    upsample2x_block_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, n, d, h, w, c);
     B21_LAUNCH_CHECK("upsample2x_block_kernel");
     return B21_OK;
   }

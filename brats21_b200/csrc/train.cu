@@ -25,7 +25,13 @@ __device__ __forceinline__ uint4 pack8t(const float* f) {
   u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// 1 / (1 + 2^(-x log2 e)) on the MUFU pipe (ex2 + rcp, flush-to-zero: no range fix-up instructions)
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 
 static inline int grid_cap(long long blocks, int per_sm = 8) {
   const long long cap = (long long)num_sms() * per_sm;
@@ -137,22 +143,39 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const __nv_bfloat1
   }
   const __nv_bfloat16* dyn = dy + size_t(n) * nvox * lddy;
   const __nv_bfloat16* zn = z + size_t(n) * nvox * ldz;
-  for (; i < total; i += T) {
-    const long long v = i / chunks;
-    float g[8], x[8];
-    unpack8t(*reinterpret_cast<const uint4*>(dyn + v * lddy + ck * 8), g);
-    unpack8t(*reinterpret_cast<const uint4*>(zn + v * ldz + ck * 8), x);
+  constexpr int U = 4;  // independent 16 B loads in flight per thread and operand
+  const long long vstep = T / chunks;  // T is a multiple of `chunks`: no 64-bit division in the loop
+  long long v0 = i / chunks;
+  for (; i < total; i += T * U, v0 += vstep * U) {
+    uint4 gv[U], xv[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (MODE == 0) {
-        const float gg = fmaf(x[j], a[j], b[j]) > 0.f ? g[j] : 0.f;
-        r1[j] += gg;
-        r2[j] = fmaf(gg, x[j], r2[j]);
-      } else {
-        const float u = x[j] * sigmoidf_fast(x[j]);
-        r1[j] += g[j];
-        r2[j] = fmaf(g[j], u, r2[j]);
-        r3[j] += u;
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * T;
+      if (iu < total) {
+        const long long v = v0 + u * vstep;
+        gv[u] = *reinterpret_cast<const uint4*>(dyn + v * lddy + ck * 8);
+        xv[u] = *reinterpret_cast<const uint4*>(zn + v * ldz + ck * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * T < total) {
+        float g[8], x[8];
+        unpack8t(gv[u], g);
+        unpack8t(xv[u], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (MODE == 0) {
+            const float gg = fmaf(x[j], a[j], b[j]) > 0.f ? g[j] : 0.f;
+            r1[j] += gg;
+            r2[j] = fmaf(gg, x[j], r2[j]);
+          } else {
+            const float uu = x[j] * sigmoidf_fast(x[j]);
+            r1[j] += g[j];
+            r2[j] = fmaf(g[j], uu, r2[j]);
+            r3[j] += uu;
+          }
+        }
       }
     }
   }
@@ -360,30 +383,49 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const __nv_bfloat16
   const __nv_bfloat16* dyn = dy + size_t(n) * nvox * lddy;
   const __nv_bfloat16* zn = z + size_t(n) * nvox * ldz;
   __nv_bfloat16* dzn = dz + size_t(n) * nvox * lddz;
-  for (; i < total; i += T) {
-    const long long v = i / chunks;
-    float g[8], x[8], o[8];
-    unpack8t(*reinterpret_cast<const uint4*>(dyn + v * lddy + ck * 8), g);
-    unpack8t(*reinterpret_cast<const uint4*>(zn + v * ldz + ck * 8), x);
+  constexpr int U = 4;  // independent 16 B loads in flight per thread and operand (dz may alias dy: own elements only)
+  const long long vstep = T / chunks;  // T is a multiple of `chunks`: no 64-bit division in the loop
+  long long v0 = i / chunks;
+  for (; i < total; i += T * U, v0 += vstep * U) {
+    uint4 gv[U], xv[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float d;
-      if (MODE == 0) {
-        d = fmaf(x[j], a[j], b[j]) > 0.f ? 1.f : 0.f;
-      } else {
-        const float s = sigmoidf_fast(x[j]);
-        d = s * fmaf(x[j], 1.f - s, 1.f);
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * T;
+      if (iu < total) {
+        const long long v = v0 + u * vstep;
+        gv[u] = *reinterpret_cast<const uint4*>(dyn + v * lddy + ck * 8);
+        xv[u] = *reinterpret_cast<const uint4*>(zn + v * ldz + ck * 8);
       }
-      o[j] = fmaf(fmaf(g[j], p0[j], p1[j]), d, fmaf(-p2[j], x[j], p3[j]));
     }
-    const uint4 pk = pack8t(o);
-    if (colsum) {
-      float q[8];
-      unpack8t(pk, q);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += q[j];
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + u * T;
+      if (iu < total) {
+        const long long v = v0 + u * vstep;
+        float g[8], x[8], o[8];
+        unpack8t(gv[u], g);
+        unpack8t(xv[u], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d;
+          if (MODE == 0) {
+            d = fmaf(x[j], a[j], b[j]) > 0.f ? 1.f : 0.f;
+          } else {
+            const float s = sigmoidf_fast(x[j]);
+            d = s * fmaf(x[j], 1.f - s, 1.f);
+          }
+          o[j] = fmaf(fmaf(g[j], p0[j], p1[j]), d, fmaf(-p2[j], x[j], p3[j]));
+        }
+        const uint4 pk = pack8t(o);
+        if (colsum) {
+          float q[8];
+          unpack8t(pk, q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += q[j];
+        }
+        *reinterpret_cast<uint4*>(dzn + v * lddz + ck * 8) = pk;
+      }
     }
-    *reinterpret_cast<uint4*>(dzn + v * lddz + ck * 8) = pk;
   }
   if (colsum) {
 #pragma unroll

@@ -39,6 +39,13 @@ def main():
     cat = torch.zeros((n, 128, 128, 128, 48), device=DEV, dtype=bf)
     report("upsample2x 24ch 64^3->128^3 (b4)", time_it(lambda: ops.upsample2x(x, cat[..., 24:])),
            x.numel() * 2 + cat.numel())
+    dense = torch.zeros((n, 128, 128, 128, 24), device=DEV, dtype=bf)
+    report("upsample2x 24ch 64^3->128^3 (b4) into a DENSE 24-ch buffer", time_it(lambda: ops.upsample2x(x, dense)),
+           x.numel() * 2 + dense.numel() * 2)
+    x32 = torch.randn((n, 64, 64, 64, 32), device=DEV).to(bf)
+    cat64 = torch.zeros((n, 128, 128, 128, 64), device=DEV, dtype=bf)
+    report("upsample2x 32ch 64^3->128^3 (b4) into half of a 64-ch buffer (sector aligned)",
+           time_it(lambda: ops.upsample2x(x32, cat64[..., 32:])), x32.numel() * 2 + cat64.numel())
     x2 = torch.randn((n, 32, 32, 32, 48), device=DEV).to(bf)
     cat2 = torch.zeros((n, 64, 64, 64, 96), device=DEV, dtype=bf)
     report("upsample2x 48ch 32^3->64^3 (b4)", time_it(lambda: ops.upsample2x(x2, cat2[..., 48:])),
