@@ -51,6 +51,7 @@ struct ConvSlideParams {
   int kc, ksteps;
   int tilesH, tilesW, segs, L, ntiles, items;
   int pslots, wstages, wsub, ks_sub;
+  int nchunks;  // input-channel chunks of 8 * kc channels (> 1: Cin >= 128, each (group, chunk) pass loads its 5 planes)
   uint32_t tap_bytes, wstage_bytes;
   FoldExtras ex;
   int variant;  // debug (B21_SLIDE_VARIANT): bit0 no plane loads, bit1 no weight loads, bit2 no epilogue math/stores, bit3 one MMA per stage
@@ -134,21 +135,29 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const SlideItem it = slide_decode(p, item);
         const int G = (it.Lc + 2) / 3;
-        const int NP = 3 * G + 2;
-        for (int j = 0; j < NP; ++j) {
-          mbar_wait_a(pempty0 + 8u * slot, phase ^ 1);
-          const uint32_t fb = pfull0 + 8u * slot;
-          if (j <= it.Lc + 1 && !(p.variant & 1)) {  // planes beyond the segment halo only feed skipped output planes: nothing to load
-            const uint32_t dst = p_addr + uint32_t(slot) * plane_bytes;
-            mbar_expect_tx_a(fb, tx);
-            for (int c = 0; c < p.kc; ++c)
-              tma_load_5d_a(dst + c * kSChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
-          } else {
-            mbar_arrive_a(fb);
-          }
-          if (++slot == p.pslots) {
-            slot = 0;
-            phase ^= 1;
+        // one chunk: the window slides across the groups of the item (3G + 2 planes); several chunks: every
+        // (group, chunk) pass loads the 5 planes of its three phases (the accumulators stay in TMEM across the chunks)
+        const int npass = p.nchunks > 1 ? G * p.nchunks : 1;
+        const int NP = p.nchunks > 1 ? 5 : 3 * G + 2;
+        for (int ps = 0; ps < npass; ++ps) {
+          const int g = p.nchunks > 1 ? ps / p.nchunks : 0;
+          const int ch0 = p.nchunks > 1 ? (ps - g * p.nchunks) * p.kc * 8 : 0;
+          for (int jj = 0; jj < NP; ++jj) {
+            const int j = 3 * g + jj;
+            mbar_wait_a(pempty0 + 8u * slot, phase ^ 1);
+            const uint32_t fb = pfull0 + 8u * slot;
+            if (j <= it.Lc + 1 && !(p.variant & 1)) {  // planes beyond the segment halo only feed skipped output planes
+              const uint32_t dst = p_addr + uint32_t(slot) * plane_bytes;
+              mbar_expect_tx_a(fb, tx);
+              for (int c = 0; c < p.kc; ++c)
+                tma_load_5d_a(dst + c * kSChunkBytes, &tmX, fb, ch0 + c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
+            } else {
+              mbar_arrive_a(fb);
+            }
+            if (++slot == p.pslots) {
+              slot = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -164,8 +173,9 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const SlideItem it = slide_decode(p, item);
         const int G = (it.Lc + 2) / 3;
-        const uint8_t* wt = p.wpk + size_t(p.ex.wstride) * it.n + size_t(it.nt) * 27 * p.tap_bytes;
-        for (int g = 0; g < G; ++g) {
+        const uint8_t* wt0 = p.wpk + size_t(p.ex.wstride) * it.n + size_t(it.nt) * p.nchunks * 27 * p.tap_bytes;
+        for (int gc = 0; gc < G * p.nchunks; ++gc) {
+          const uint8_t* wt = wt0 + size_t(gc % p.nchunks) * 27 * p.tap_bytes;
           for (int tap = 0; tap < 27; ++tap) {  // tap = kd * 9 + kh * 3 + kw: phase kd walks taps kd*9 .. kd*9+8
             for (int sub = 0; sub < kWsub; ++sub) {
               mbar_wait_a(wempty0 + 8u * ws, wph ^ 1);
@@ -206,7 +216,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       const uint32_t plane16 = plane_bytes >> 4, wstage16 = p.wstage_bytes >> 4;
       const uint32_t idesc = umma_idesc_bf16(128, NT);
       constexpr uint32_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);  // one k-step (16 channels), 16 B units
-      const int pslots = p.pslots, wstages = p.wstages;
+      const int pslots = p.pslots, wstages = p.wstages, nchunks = p.nchunks;
       int pwait_slot = 0;        // next plane slot to wait for (planes are consumed strictly in ring order)
       uint32_t pwait_ph = 0;
       int win_slot = 0;          // ring slot of plane j = phi (first plane of the current window)
@@ -224,8 +234,10 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           uint32_t as2 = as1 + 1, ap2 = ap1;
           if (as2 == RING) { as2 = 0; ap2 ^= 1u; }
           const uint32_t dcol0 = tmem_base + acc_slot * NT, dcol1 = tmem_base + as1 * NT, dcol2 = tmem_base + as2 * NT;
+          for (int ch = 0; ch < nchunks; ++ch) {
+          if (nchunks > 1) jwait = 0;  // every (group, chunk) pass has its own 5 planes
           for (int kd = 0; kd < 3; ++kd) {
-            const int phi = 3 * g + kd;
+            const int phi = nchunks > 1 ? kd : 3 * g + kd;
             while (jwait <= phi + 2) {
               mbar_wait_a(pfull0 + 8u * pwait_slot, pwait_ph);
               if (++pwait_slot == pslots) {
@@ -246,7 +258,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
                 const uint32_t tap16 = uint32_t(kh * kSHW + kw);
-                const uint32_t fresh = (kd | kh | kw) == 0 ? 1u : 0u;  // first contribution to the group's accumulators
+                const uint32_t fresh = (ch | kd | kh | kw) == 0 ? 1u : 0u;  // first contribution to the group's accumulators
                 {
                   mbar_wait_a(wfull0 + 8u * ws, wph);
                   tc_fence_after();
@@ -300,6 +312,13 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
             umma_commit_a(pempty0 + 8u * win_slot);  // plane j = phi has served its last window
             win_slot = s1;
           }
+          if (nchunks > 1) {  // the two trailing planes of the pass
+            umma_commit_a(pempty0 + 8u * win_slot);
+            if (++win_slot == pslots) win_slot = 0;
+            umma_commit_a(pempty0 + 8u * win_slot);
+            if (++win_slot == pslots) win_slot = 0;
+          }
+          }
           for (int r = 0; r < nvalid; ++r) {  // the group's accumulators are complete
             umma_commit_a(accf0 + 8u * acc_slot);
             if (++acc_slot == RING) {
@@ -308,11 +327,12 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
             }
           }
         }
-        // the two trailing halo planes (j = 3G, 3G+1)
-        umma_commit_a(pempty0 + 8u * win_slot);
-        if (++win_slot == pslots) win_slot = 0;
-        umma_commit_a(pempty0 + 8u * win_slot);
-        if (++win_slot == pslots) win_slot = 0;
+        if (nchunks == 1) {  // the two trailing halo planes (j = 3G, 3G+1)
+          umma_commit_a(pempty0 + 8u * win_slot);
+          if (++win_slot == pslots) win_slot = 0;
+          umma_commit_a(pempty0 + 8u * win_slot);
+          if (++win_slot == pslots) win_slot = 0;
+        }
       }
     }
   } else {
@@ -445,14 +465,14 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
 __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout_o,
                                          int cin_o, int rows, int kc, int nt, int transpose_flip,
                                          const float* __restrict__ scale = nullptr, int ldscale = 0,
-                                         int pack_blocks = 0, BiasTableArgs tab = BiasTableArgs()) {
+                                         int pack_blocks = 0, BiasTableArgs tab = BiasTableArgs(), int nchunks = 1) {
   if (pack_blocks > 0 && int(blockIdx.x) >= pack_blocks) {  // appended blocks: one bias-table row each
     bias_table_block(tab, blockIdx.x - pack_blocks, blockIdx.y);
     return;
   }
   const int ng = nt / 8;
   const int ntiles = rows / nt;
-  const size_t total = size_t(ntiles) * 27 * kc * ng * 64;
+  const size_t total = size_t(ntiles) * nchunks * 27 * kc * ng * 64;  // kc = 8-channel chunks per input-channel chunk
   const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
@@ -461,10 +481,11 @@ __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloa
     size_t t = i >> 6;
     const int g = int(t % ng); t /= ng;
     const int c = int(t % kc); t /= kc;
-    const int tap = int(t % 27);
-    const int tile = int(t / 27);
+    const int tap = int(t % 27); t /= 27;
+    const int chunk = int(t % nchunks);
+    const int tile = int(t / nchunks);
     const int ro = tile * nt + g * 8 + n8;
-    const int ki = c * 8 + k8;
+    const int ki = (chunk * kc + c) * 8 + k8;
     float v = 0.f;
     if (!transpose_flip) {
       if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap] * (scale ? scale[ki] : 1.f);
@@ -475,19 +496,22 @@ __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloa
   }
 }
 
-static inline int slide_kc(int cin) { return (cin + 15) / 16 * 2; }
+static inline int slide_nchunks(int cin) { return cin > 96 ? cin / 64 : 1; }
+static inline int slide_kc(int cin) { return cin > 96 ? 8 : (cin + 15) / 16 * 2; }  // 8-channel chunks per channel chunk
 static inline int slide_nt(int cout) { return cout % 96 == 0 ? 96 : (cout % 48 == 0 ? 48 : (cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0))); }
 
 struct SlideCfg {
-  int kc, ksteps, nt, wsub, ks_sub, pslots, wstages;
+  int kc, ksteps, nt, wsub, ks_sub, pslots, wstages, nchunks;
   uint32_t tap_bytes, wstage_bytes;
   size_t smem_bytes;
 };
 static bool slide_config(int cin, int cout, SlideCfg* c) {
-  if (cin < 16 || cin > 96 || cin % 8 || cout % 8) return false;
+  if (cin < 16 || cin % 8 || cout % 8) return false;
+  if (cin > 96 && cin % 64) return false;  // channel-chunked mode: whole 64-channel chunks
   c->nt = slide_nt(cout);
   if (c->nt == 0) return false;
   if ((cout / 8) == 0 || c->nt % (cout / 8) != 0) return false;  // whole norm groups per N tile
+  c->nchunks = slide_nchunks(cin);
   c->kc = slide_kc(cin);
   c->ksteps = c->kc / 2;
   c->tap_bytes = uint32_t(c->kc) * c->nt * 16u;
@@ -495,9 +519,11 @@ static bool slide_config(int cin, int cout, SlideCfg* c) {
   c->ks_sub = c->wsub == 2 ? (c->ksteps + 1) / 2 : c->ksteps;
   c->wstage_bytes = (uint32_t(c->ks_sub) * c->nt * 32u + 127u) & ~127u;
   const size_t plane = size_t(c->kc) * kSChunkBytes;
-  c->pslots = 5;
-  if (size_t(kSSmemBudget) < 128 + 5 * plane + 2 * size_t(c->wstage_bytes)) return false;
-  size_t ws = (size_t(kSSmemBudget) - 128 - 5 * plane) / c->wstage_bytes;
+  // one chunk: 3 planes in use + 2 in flight; several chunks: a pass needs its third plane while the previous pass still
+  // holds three, so one more slot keeps the pipeline full
+  c->pslots = c->nchunks > 1 ? 6 : 5;
+  if (size_t(kSSmemBudget) < 128 + c->pslots * plane + 2 * size_t(c->wstage_bytes)) return false;
+  size_t ws = (size_t(kSSmemBudget) - 128 - c->pslots * plane) / c->wstage_bytes;
   c->wstages = int(ws > size_t(kSMaxWStages) ? size_t(kSMaxWStages) : ws);
   if (c->wstages < (c->wsub == 2 ? 3 : 2)) return false;
   // spare room -> extra plane slots (deeper halo prefetch)
@@ -526,7 +552,9 @@ static int launch_slide(const CUtensorMap& tm, const ConvSlideParams& p, size_t 
 //   96 -> 96   EquiUNet-ASPP-Evo encoder2/decoder2 (+ data gradients), EquiUNet encoder2.2
 //   48 -> 96   EquiUNet encoder2.1;  96 -> 48  EquiUNet decoder1.1 / decoder2.2;  96 -> 192  EquiUNet encoder3.1
 //   64 -> 64   level 3 of the width-16 networks the parity tests run
-#define B21_SLIDE_SHAPES(X) X(96, 12, 3, 3) X(96, 12, 3, 0) X(48, 6, 3, 3) X(96, 24, 3, 3) X(64, 8, 2, 2)
+//   192 -> 192, 384 -> 384, 192 -> 96, 384 -> 192, 768 -> 192 ...: channel-chunked mode (64-channel chunks: KS 2 + 2)
+#define B21_SLIDE_SHAPES(X) \
+  X(96, 12, 3, 3) X(96, 12, 3, 0) X(48, 6, 3, 3) X(96, 24, 3, 3) X(64, 8, 2, 2) X(96, 12, 2, 2) X(96, 24, 2, 2) X(96, 48, 2, 2)
 
 static bool slide_instantiated(const SlideCfg& c, int cout) {
   const int gs = cout / 8, ks1 = c.ksteps - c.ks_sub;
@@ -547,7 +575,7 @@ extern "C" int b21_conv_slide_supported(int cin, int cout) {
 }
 
 extern "C" long long b21_conv_slide_weight_bytes(int cin, int cout) {
-  return (long long)27 * slide_kc(cin) * cout * 16;
+  return (long long)27 * slide_nchunks(cin) * slide_kc(cin) * cout * 16;
 }
 
 extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout, int cin, int transpose_flip,
@@ -556,11 +584,12 @@ extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout
   const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
   SlideCfg c;
   B21_CHECK_ARG(slide_config(inner, rows, &c), "pack_conv_weight_slide: (cin %d, cout %d) unsupported", inner, rows);
-  const size_t total = size_t(27) * c.kc * rows * 8;
+  const size_t total = size_t(27) * c.nchunks * c.kc * rows * 8;
   const int threads = 256;
   const int blocks = int((total + threads - 1) / threads) < 2048 ? int((total + threads - 1) / threads) : 2048;
   pack_slide_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, c.kc, c.nt, transpose_flip);
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, c.kc, c.nt, transpose_flip, nullptr, 0, 0,
+      BiasTableArgs(), c.nchunks);
   B21_LAUNCH_CHECK("pack_slide_weight_kernel");
   return B21_OK;
 }
@@ -572,12 +601,12 @@ extern "C" int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int
   B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_slide_fold: the bias table needs ws and B");
   SlideCfg c;
   B21_CHECK_ARG(slide_config(cin, cout, &c), "pack_conv_weight_slide_fold: (cin %d, cout %d) unsupported", cin, cout);
-  const size_t total = size_t(27) * c.kc * cout * 8;
+  const size_t total = size_t(27) * c.nchunks * c.kc * cout * 8;
   const int threads = 256;
   const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
   BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, 27};
   pack_slide_weight_kernel<<<dim3(bx + (table ? 27 : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale, bx, tab);
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale, bx, tab, c.nchunks);
   B21_LAUNCH_CHECK("pack_slide_weight_kernel(fold)");
   return B21_OK;
 }
@@ -628,6 +657,7 @@ static int slide_fwd_impl(const void* x, int ldx, const void* w_slide, const flo
   p.ntiles = cout / c.nt;
   p.pslots = c.pslots; p.wstages = c.wstages; p.wsub = c.wsub; p.ks_sub = c.ks_sub;
   p.tap_bytes = c.tap_bytes; p.wstage_bytes = c.wstage_bytes;
+  p.nchunks = c.nchunks;
   p.ex = ex;
   static int variant = -1;
   if (variant < 0) {

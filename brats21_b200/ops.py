@@ -81,7 +81,9 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
         kind = "march"
         call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())
-    elif use_slide and dil == 1 and pw.w_slide is not None and h >= 8 and w >= 8:
+    elif use_slide and dil == 1 and pw.w_slide is not None and h >= 8 and w >= 8 and (cin <= 96 or h * w >= 1024):
+        # (channel-chunked mode, cin >= 128: the 16^3 level has too few tiles to balance the persistent grid — measured
+        # 754 vs 891 TFLOP/s for 384 -> 384 — and stays on the tap kernel)
         kind = "slide"
         call("b21_conv3d_slide_fwd", ptr(x), _ld(x), ptr(pw.w_slide), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d, h, w, cin, pw.cout, stream_ptr())

@@ -89,7 +89,10 @@ def test_conv1x1_persistent_matches_torch_and_tap_kernel(cin, cout, shape):
 @pytest.mark.parametrize("cin,cout,shape", [
     (96, 96, (1, 8, 16, 8)), (96, 96, (2, 7, 20, 12)), (96, 96, (1, 32, 32, 32)), (48, 96, (1, 9, 16, 16)),
     (96, 48, (1, 10, 8, 24)), (64, 64, (2, 5, 9, 11)), (96, 192, (1, 4, 16, 8)), (96, 96, (1, 3, 8, 8)),
-    (96, 48, (1, 13, 17, 9))])
+    (96, 48, (1, 13, 17, 9)),
+    # channel-chunked mode (Cin >= 128: 64-channel chunks, accumulators persist across the chunk passes)
+    (192, 192, (1, 8, 16, 16)), (192, 192, (2, 7, 9, 12)), (384, 384, (1, 4, 8, 8)), (192, 96, (1, 5, 16, 8)),
+    (384, 192, (1, 6, 8, 16)), (128, 64, (1, 10, 8, 8)), (768, 192, (1, 3, 8, 8))])
 def test_conv3d_slide_matches_torch(cin, cout, shape):
     """conv_slide.cu (smem-resident halo planes, streamed weight taps, 3 output planes per tap) against torch fp32,
     reading/writing channel slices of wider buffers, with ragged tiles, several d-segments and samples."""
