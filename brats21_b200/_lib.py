@@ -66,6 +66,15 @@ _SIGNATURES = {
     "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp],
     "b21_ranger_chunk": [],
     "b21_ranger_step": [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
+    "b21_grad_centralize": [_vp, _i, _vp],
+    "b21_foreground_bbox": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "b21_nonzero_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "b21_normalize_crop_pad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "b21_keep_components_workspace_bytes": [_i64],
+    "b21_keep_components": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "b21_replace_rare_workspace_bytes": [_i],
+    "b21_replace_rare_labels": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b21_labels_to_channels": [_vp, _vp, _i64, _vp],
 }
 
 _lib = None
@@ -96,6 +105,8 @@ def load():
         fn.restype = _i
     lib.b21_conv_march_weight_bytes.restype = C.c_longlong
     lib.b21_conv_slide_weight_bytes.restype = C.c_longlong
+    lib.b21_keep_components_workspace_bytes.restype = C.c_longlong
+    lib.b21_replace_rare_workspace_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -119,7 +130,9 @@ def stream_ptr():
 
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
-             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2}
+             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2,
+             "b21_keep_components_workspace_bytes": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
+             "b21_keep_components": 4, "b21_replace_rare_labels": 5}
 launch_count = 0
 
 

@@ -63,3 +63,37 @@ extern "C" int b21_ranger_step(const long long* table, const int* chunks, int nc
   B21_LAUNCH_CHECK("ranger_step_kernel");
   return B21_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient centralisation (centralized_gradient, learning/optimizer.py:11-20; gc_loc = True: applied to the raw
+// gradient before the moment updates, optimizer.py:187-188): every dim-0 slice ("row") of a qualifying gradient
+// tensor has its mean subtracted in place.  rows: int64 [nrows][2] = {pointer to the row, row length}; one CTA per row.
+namespace b21 {
+__global__ void __launch_bounds__(256) grad_centralize_kernel(const long long* __restrict__ rows) {
+  float* g = reinterpret_cast<float*>(rows[size_t(blockIdx.x) * 2]);
+  const int n = int(rows[size_t(blockIdx.x) * 2 + 1]);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += g[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[8];
+  __shared__ float mean_s;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    mean_s = t / float(n);
+  }
+  __syncthreads();
+  const float m = mean_s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] -= m;
+}
+}  // namespace b21
+
+extern "C" int b21_grad_centralize(const long long* rows, int nrows, void* stream) {
+  B21_CHECK_ARG(rows && nrows > 0, "grad_centralize: empty row table");
+  b21::grad_centralize_kernel<<<nrows, 256, 0, (cudaStream_t)stream>>>(rows);
+  B21_LAUNCH_CHECK("grad_centralize_kernel");
+  return B21_OK;
+}

@@ -30,13 +30,14 @@ class Ranger2020(Optimizer):
             raise ValueError(f'Invalid Learning Rate: {lr}')
         if not eps > 0:
             raise ValueError(f'Invalid eps: {eps}')
-        if use_gc or use_gcnorm or normloss_active:
-            raise NotImplementedError("gradient centralisation / norm loss are off in the reference recipe "
-                                      "(README.md:103-121) and not on the fused path")
+        if use_gcnorm or normloss_active or (use_gc and not gc_loc):
+            raise NotImplementedError("gradient normalisation / norm loss / post-moment centralisation are off in "
+                                      "the reference recipe (README.md:103-121) and not on the fused path")
         defaults = dict(lr=lr, alpha=alpha, k=k, step_counter=0, betas=betas, N_sma_threshhold=N_sma_threshhold, eps=eps,
                         weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.N_sma_threshhold, self.alpha, self.k = N_sma_threshhold, alpha, k
+        self.use_gc, self.gc_conv_only = use_gc, gc_conv_only
         self.grad_scale = 1.0
         self._tables = {}
 
@@ -55,8 +56,17 @@ class Ranger2020(Optimizer):
         dev = plist[0].device
         table = torch.tensor(rows, dtype=torch.int64, device=dev)
         ctab = torch.tensor(chunks, dtype=torch.int32, device=dev)
-        self._tables[gi] = (key, table, ctab)
-        return table, ctab
+        gc_rows = None
+        if self.use_gc:  # centralized_gradient (optimizer.py:11-20): one row per dim-0 slice of qualifying tensors
+            min_dim = 3 if self.gc_conv_only else 1
+            rr = []
+            for p in plist:
+                if p.dim() > min_dim:
+                    rl = p.numel() // p.shape[0]
+                    rr += [[p.grad.data_ptr() + 4 * rl * i, rl] for i in range(p.shape[0])]
+            gc_rows = torch.tensor(rr, dtype=torch.int64, device=dev) if rr else None
+        self._tables[gi] = (key, table, ctab, gc_rows)
+        return table, ctab, gc_rows
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -91,7 +101,9 @@ class Ranger2020(Optimizer):
                                       (n_sma_max - 2)) / (1 - beta1 ** step)
             else:
                 step_size = 1.0 / (1 - beta1 ** step)
-            table, ctab = self._table(gi, plist)
+            table, ctab, gc_rows = self._table(gi, plist)
+            if gc_rows is not None:
+                call("b21_grad_centralize", ptr(gc_rows), gc_rows.shape[0], stream_ptr())
             call("b21_ranger_step", ptr(table), ptr(ctab), ctab.shape[0], float(self.grad_scale), float(group["lr"]),
                  float(step_size), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
                  int(rect), int(step % group["k"] == 0), float(self.alpha), stream_ptr())

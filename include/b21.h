@@ -256,6 +256,42 @@ int b21_ranger_step(const long long* table, const int* chunks, int nchunks, floa
                     float beta1, float beta2, float eps, float weight_decay, int rectified, int lookahead, float alpha,
                     void* stream);
 
+/* Gradient centralisation (centralized_gradient, learning/optimizer.py:11-20, applied at optimizer.py:187-188 when
+ * use_gc): every dim-0 slice of a qualifying gradient tensor has its mean subtracted in place, before
+ * b21_ranger_step.  rows: int64 [nrows][2] = {device pointer to the fp32 row, row length}. */
+int b21_grad_centralize(const long long* rows, int nrows, void* stream);
+
+/* ------------------------------------------------------------------------------------- input side (pre.cu)
+ * CropForegroundd + NormalizeIntensityd(nonzero, channel_wise[, remove_outliers]) + shape_to_divisible(k)
+ * (src/definer.py:561-567, utils/transforms.py:328-406,483-512) on an fp32 [c][d][h][w] device volume.
+ * bbox (device int[6]) = {min d, min h, min w, max d+1, max h+1, max w+1} of the voxels where any channel > 0
+ * ({d, h, w, 0, 0, 0} when there is none).  stats (device double [c][3]) = {count, sum, sum of squares} of the
+ * voxels != 0 inside bbox.  b21_normalize_crop_pad writes out[c][od][oh][ow]: the box, shifted by (pad_d, pad_h,
+ * pad_w), zero elsewhere; non-zero voxels become (x - mean) / std (population std, 0 -> 1), clipped to +-clip when
+ * clip > 0 (remove_outliers); zeros stay zero. */
+int b21_foreground_bbox(const float* img, int c, int d, int h, int w, int* bbox, void* stream);
+int b21_nonzero_stats(const float* img, int c, int d, int h, int w, const int* bbox, double* stats, void* stream);
+int b21_normalize_crop_pad(const float* img, float* out, int c, int d, int h, int w, const int* bbox,
+                           const double* stats, int od, int oh, int ow, int pad_d, int pad_h, int pad_w, float clip,
+                           void* stream);
+
+/* --------------------------------------------------------------------------- label post-processing (post.cu)
+ * b21_keep_components: KeepLargestConnectedComponent / get_largest_component (utils/transforms.py:209-230,579-600)
+ * on a uint8 label map [d][h][w], in place: components of (label != 0) under full 26-connectivity
+ * (skimage.morphology.label default) with at most `threshold` voxels are zeroed; threshold < 0 keeps only the
+ * largest component (the first in raster order on ties).  work: b21_keep_components_workspace_bytes(nvox) bytes.
+ * b21_replace_rare_labels: ReplaceWithClosestValue (utils/transforms.py:233-268,603-647), in place: every label
+ * value carried by at most `thresh` voxels is replaced — provided at least one NON-ZERO value is that rare — by the
+ * value of the nearest voxel (euclidean, inside the 2-D slice orthogonal to `axis`) with a kept label; equidistant
+ * candidates: the smallest row-major slice index.  dims (n0, n1, n2) are those of the squeezed label map.
+ * b21_labels_to_channels: MONAI ConvertToMultiChannelBasedOnBratsClasses: uint8 [3][nvox] = (TC = 1|4, WT = 1|2|4,
+ * ET = 4) (definer.py:691). */
+long long b21_keep_components_workspace_bytes(long long nvox);
+int b21_keep_components(uint8_t* label, void* work, int d, int h, int w, int threshold, void* stream);
+long long b21_replace_rare_workspace_bytes(int thresh);
+int b21_replace_rare_labels(uint8_t* label, void* work, int n0, int n1, int n2, int thresh, int axis, void* stream);
+int b21_labels_to_channels(const uint8_t* label, uint8_t* onehot, long long nvox, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
