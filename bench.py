@@ -8,6 +8,8 @@ One *step* = one full pass of the hot path over one synthetic 4x240x240x155 volu
       EquiUNet-ASPP-Evo (width 48), 8 axis-flip TTA variants, 128^3 sliding window (overlap 0.25 -> 18 windows per
       variant, 144 per volume, batches of 4), gaussian blending, sigmoid/mean/threshold, BraTS label map.
   workload "v1_sw"  (configs[1]): EquiUNet V1, no TTA, same window grid, batches of 4.
+  workload "v2_ens3_tta8" (configs[4]): three EquiUNet-ASPP-Evo models x 8 flips per volume (432 windows), cohort
+      volumes sharded across ranks.   workload "v2_train" (configs[3]): one training step, batch 1 per GPU.
 `value` is whole-job volumes/s with the volume resident in HBM; `e2e` is the same through the public API
 (brats21_b200.engine.predict_volume) from a pinned HOST volume to HOST uint8 labels, copies inside the timed region.
 Multi-GPU (torchrun): volumes are sharded across ranks, no data-path collective ("weak" scaling).
@@ -37,6 +39,9 @@ WORKLOADS = {
     "v2_tta8": dict(version=2, tta="flip8", mode="gaussian", sw_batch=4, seed=93,
                     desc="EquiUNet-ASPP-Evo w48, 8-flip TTA, 128^3 sliding window (144 windows), gaussian blend, "
                          "labels; one synthetic 4x240x240x155 volume per step"),
+    "v2_ens3_tta8": dict(version=2, tta="flip8", mode="gaussian", sw_batch=4, seed=93, ensemble=(93, 123, 7),
+                         desc="Model-6-style ensemble of 3 EquiUNet-ASPP-Evo w48 x 8-flip TTA (432 windows per volume), "
+                              "gaussian blend, mean over 24 probability maps, labels; cohort volumes sharded across ranks"),
     "v1_sw": dict(version=1, tta=None, mode="constant", sw_batch=4, seed=123,
                   desc="EquiUNet V1 w48, no TTA, 128^3 sliding window (18 windows, batches of 4), labels"),
     "v2_train": dict(version=2, train=True, seed=93,
@@ -128,7 +133,7 @@ def cpu_window_forward_seconds(version: int, repeats: int = 1, shape=ROI):
 
 
 def windows_per_volume(wl):
-    return 18 * (8 if wl["tta"] == "flip8" else 1)
+    return 18 * (8 if wl["tta"] == "flip8" else 1) * len(wl.get("ensemble", (0,)))
 
 
 def run_reference(args, wl, rank, world):
@@ -268,13 +273,15 @@ def run_b200(args, wl, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     from brats21_b200 import _lib, engine, networks, ops, synth, tta
 
-    torch.manual_seed(wl["seed"])
     feats = [WIDTH * 2 ** i for i in range(4)]
     cls = networks.EquiUnetASSPEvo if wl["version"] == 2 else networks.EquiUnet
     import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        net = cls(4, 3, feats, norm_layer="group", act="relu", deep_supervision=True).to(dev).eval()
+    nets = []
+    for seed in wl.get("ensemble", (wl["seed"],)):  # the reference's seeds (arguments_train.py:103) + 7
+        torch.manual_seed(seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            nets.append(cls(4, 3, feats, norm_layer="group", act="relu", deep_supervision=True).to(dev).eval())
     comp = tta.get_flip8_transforms() if wl["tta"] == "flip8" else None
 
     host_vol = synth.volume(seed=1000 + rank, shape=VOL_SHAPE).pin_memory()
@@ -282,11 +289,11 @@ def run_b200(args, wl, rank, local_rank, world):
     vol_dev, _ = pad_to_8(host_vol.to(dev))
 
     def step_device():
-        return engine.predict_volume([net], vol_dev, comp, True, ROI, wl["sw_batch"], 0.25, wl["mode"])
+        return engine.predict_volume(nets, vol_dev, comp, True, ROI, wl["sw_batch"], 0.25, wl["mode"])
 
     def step_e2e():
         v, meta = pad_to_8(host_vol.to(dev, non_blocking=True))
-        _, label = engine.predict_volume([net], v, comp, True, ROI, wl["sw_batch"], 0.25, wl["mode"])
+        _, label = engine.predict_volume(nets, v, comp, True, ROI, wl["sw_batch"], 0.25, wl["mode"])
         crop = label[..., meta[0][0]:meta[0][0] + meta[0][1], meta[1][0]:meta[1][0] + meta[1][1],
                      meta[2][0]:meta[2][0] + meta[2][1]]
         host_lab.copy_(crop, non_blocking=True)

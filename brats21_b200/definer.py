@@ -46,12 +46,28 @@ def get_activation():
 
 
 def get_post_transforms(args: argparse.Namespace):
-    """AsDiscrete(threshold_values=True, logit_thresh=...) (definer.py:671-697); the label-cleaning options
-    (connected components / closest-value replacement) are CPU graph algorithms outside the hot path."""
-    if getattr(args, "replace_value", False) or getattr(args, "cleaning_areas", False):
-        raise NotImplementedError("connected-component cleaning / value replacement are out of scope (SURVEY §8f)")
+    """src/definer.py:671-697.  Plain case: AsDiscrete(threshold_values=True, logit_thresh).  With
+    ``args.cleaning_areas`` / ``args.replace_value``: threshold -> BraTS label map (3 -> 4) -> connected-component
+    size filter -> rare-label replacement -> back to (TC, WT, ET) channels, all on the GPU (postprocess.py)."""
     thresh = getattr(args, "logit_threshold", 0.5)
-    return lambda x: (x >= thresh).float()
+    cleaning = getattr(args, "cleaning_areas", False)
+    replace = getattr(args, "replace_value", False)
+    if not (cleaning or replace):
+        return lambda x: (x >= thresh).float()
+    from . import ops, postprocess
+
+    def post(prob):
+        if prob.dim() != 5 or prob.shape[0] != 1 or prob.shape[1] != 3:
+            raise AssertionError("Number of channel need to be 3 (TC/WT/ET), batch 1")
+        _, label = ops.labels_finalize(prob[0].contiguous().float(), 1.0, thresh, want_onehot=False)
+        label = label[None, None]
+        if cleaning:
+            label = postprocess.KeepLargestConnectedComponent(getattr(args, "cleaning_areas_threshold", 10))(label)
+        if replace:
+            label = postprocess.ReplaceWithClosestValue(labels=[3], thresh=getattr(args, "replace_value_threshold", 20))(label)
+        return postprocess.labels_to_channels(label).float()
+
+    return post
 
 
 def make_criterion(args: argparse.Namespace):

@@ -133,3 +133,26 @@ def predict_volume(models: Sequence, image: torch.Tensor, tta_transforms: Option
     if return_prob:
         return onehot[None], label[None, None], prob_sum / count
     return onehot[None], label[None, None]
+
+
+@torch.no_grad()
+def predict_case(models: Sequence, raw_image: torch.Tensor, tta_transforms: Optional[Compose] = None,
+                 roi_size=(128, 128, 128), sw_batch_size: int = 4, overlap: float = 0.25, mode: str = "gaussian",
+                 logit_thresh: float = 0.5, cleaning_areas_threshold: Optional[int] = None,
+                 replace_value_threshold: Optional[int] = None, remove_outliers: bool = False):
+    """Raw intensities -> BraTS label map at the ORIGINAL image size, everything on the GPU: the reference's
+    inference flow src/definer.py:561-567 (CropForegroundd, NormalizeIntensityd) -> learning/engine.py:226-252
+    (shape_to_divisible, ensemble x TTA x sliding window, mean, threshold, background removal) -> post transforms
+    (definer.py:679-692, optional) -> shape_to_original + pad_back_to_shape_before_compose (engine.py:258-262).
+
+    raw_image: [C, D, H, W] fp32 on CUDA.  Returns uint8 [D, H, W] with labels 0/1/2/4.
+    """
+    from . import postprocess, preprocess
+    vol, meta = preprocess.crop_normalize_pad(raw_image, 8, remove_outliers=remove_outliers)
+    _, label = predict_volume(models, vol, tta_transforms, True, roi_size, sw_batch_size, overlap, mode,
+                              logit_thresh=logit_thresh)
+    if cleaning_areas_threshold is not None:
+        label = postprocess.KeepLargestConnectedComponent(cleaning_areas_threshold)(label)
+    if replace_value_threshold is not None:
+        label = postprocess.ReplaceWithClosestValue(labels=[3], thresh=replace_value_threshold)(label)
+    return postprocess.pad_back(label[0, 0], meta)

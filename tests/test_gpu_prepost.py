@@ -160,3 +160,65 @@ def test_ranger_gradient_centralisation_matches_reference_golden(golden_dir):
             for i, p in enumerate(ps):
                 ref = torch.from_numpy(g[f"gc_s{step + 1}_p{i}"])
                 assert (p.detach().cpu() - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def test_predict_case_end_to_end_matches_oracle_chain():
+    """Raw intensities -> labels at the original size through engine.predict_case, against the oracle chain
+    (crop/normalise/pad -> V2 sliding window with 8 flips -> mean/threshold/background -> component filter -> pad
+    back).  Labels are compared outside the 0.02 probability margin (bf16 network vs fp32 oracle)."""
+    from brats21_b200 import engine, networks, tta
+    from oracle import inference as oinf
+    from oracle import nets, synth
+    from oracle import prepost as pp
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    width = 16
+    params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
+    net = networks.EquiUnetASSPEvo(4, 3, [width * 2 ** i for i in range(4)], deep_supervision=True).to(DEV).eval()
+    net.load_state_dict(params)
+    raw = pp.synth_raw(5, (4, 50, 44, 41))
+    got = engine.predict_case([net], torch.from_numpy(raw).to(DEV), tta.get_flip8_transforms(), (32, 32, 32), 2,
+                              cleaning_areas_threshold=10)
+    assert got.shape == raw.shape[1:] and got.dtype == torch.uint8
+    vol, start, end, pb, pa = pp.preprocess(raw, 8)
+    v = torch.from_numpy(vol)[None]
+    with torch.no_grad():
+        fwd = lambda z: nets.equiunet_v2_forward(params, z.to(DEV))[0].cpu()  # noqa: E731
+        outs = oinf.apply_tta(lambda z: oinf.sliding_window_inference(z.contiguous(), (32, 32, 32), 2, fwd, 0.25,
+                                                                      "gaussian"), v, oinf.flip8_tta())
+        prob, hard = oinf.ensemble_mean_threshold(outs)
+        hard = oinf.remove_background_voxels(v, hard)
+    margin_ok = ((prob - 0.5).abs() > 0.02).all(dim=1)[0].numpy()
+    lab = pp.brats_label_map(hard[0].numpy())
+    # voxels inside the margin may legitimately differ and, through them, so may component sizes: compare the
+    # un-cleaned maps voxel-wise and the cleaned ones only when nothing sits inside the margin of a small component
+    plain = engine.predict_case([net], torch.from_numpy(raw).to(DEV), tta.get_flip8_transforms(), (32, 32, 32), 2)
+    core = lab[pb[0]:lab.shape[0] - pa[0], pb[1]:lab.shape[1] - pa[1], pb[2]:lab.shape[2] - pa[2]]
+    full = np.zeros(raw.shape[1:], dtype=np.uint8)
+    full[start[0]:end[0], start[1]:end[1], start[2]:end[2]] = core
+    mfull = np.ones(raw.shape[1:], dtype=bool)
+    mfull[start[0]:end[0], start[1]:end[1], start[2]:end[2]] = \
+        margin_ok[pb[0]:lab.shape[0] - pa[0], pb[1]:lab.shape[1] - pa[1], pb[2]:lab.shape[2] - pa[2]]
+    p = plain.cpu().numpy()
+    assert np.array_equal(p[mfull], full[mfull])
+    assert p[~np.any(raw != 0, axis=0)].max() == 0  # background removed, zero outside the crop box
+    # the cleaned result equals the oracle's component filter applied to OUR un-cleaned map (integer stage: exact)
+    assert np.array_equal(got.cpu().numpy(), pp.get_largest_component(p, 10))
+
+
+def test_post_transforms_factory_with_cleaning():
+    import argparse
+    from brats21_b200 import definer
+    from oracle import prepost as pp
+    lab = pp.synth_labels(4)
+    onehot = pp.labels_to_channels(lab).astype(np.float32)
+    prob = torch.from_numpy(onehot * 0.9 + 0.05)[None].to(DEV)
+    args = argparse.Namespace(cleaning_areas=True, cleaning_areas_threshold=10, replace_value=True,
+                              replace_value_threshold=20)
+    out = definer.get_post_transforms(args)(prob)
+    ref = pp.get_largest_component(lab, 10)
+    ref, amb = pp.replace_with_closest_value(ref, 20, 2)
+    assert out.shape == (1, 3) + lab.shape and out.dtype == torch.float32
+    assert np.array_equal(out[0].cpu().numpy().astype(np.uint8), pp.labels_to_channels(ref))
+    plain = definer.get_post_transforms(argparse.Namespace())(prob)
+    assert np.array_equal(plain[0].cpu().numpy(), onehot)
