@@ -28,7 +28,11 @@
 
 namespace b21 {
 
-constexpr int kMThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 and 6..9: two epilogue groups (alternate planes)
+// warp 0 TMA, warp 1 MMA, then NG epilogue groups of four warps (planes are dealt round-robin to the groups).
+// NG = 2 (320 threads) everywhere except the Cin = 8 input conv: with 9 MMAs per plane its epilogue (about 800
+// instructions per warp and plane, issue-latency bound at 2 warps per scheduler: 2000 cycles per plane against 650 of
+// MMAs) is the bottleneck, so it runs NG = 4 groups (576 threads, <= 112 registers: 16-column passes).
+constexpr int kMThreadsBase = 64;
 constexpr int kMTH = 16, kMTW = 8;                // in-plane output tile: M = 128 rows = 16 h x 8 w
 constexpr int kMHH = kMTH + 2, kMHW = kMTW + 2;   // halo plane 18 x 10
 constexpr int kMChunkData = kMHH * kMHW * 16;     // one 8-channel chunk of a halo plane (2880 B of TMA payload)
@@ -48,6 +52,7 @@ struct ConvMarchParams {
   int stages, ring;
   uint32_t wbytes;
   FoldExtras ex;
+  int merged;   // Cin == 8 dense input (ld = 8): (w, c) merged into one tensor-map dimension, chunk 1 is zero in smem
   int variant;  // debug (B21_MARCH_VARIANT): bit2 no TMA loads, bit3 no stores, bit4 three taps only, bit5 no epilogue math/stores, bit6 no TMEM ld/st
 };
 
@@ -72,9 +77,11 @@ __device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int i
   return it;
 }
 
-template <int COUT>
-__global__ void __launch_bounds__(kMThreads, 1)
+template <int COUT, int NG>
+__global__ void __launch_bounds__(kMThreadsBase + NG * 128, 1)
 conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams p) {
+  constexpr int kMThreads = kMThreadsBase + NG * 128;
+  constexpr int PC = NG > 2 ? 16 : COUT;  // columns per epilogue pass
   constexpr uint32_t RING = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;  // accumulator slots in TMEM
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMMaxStages];
@@ -83,7 +90,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
   __shared__ __align__(8) uint64_t acce_bar[kMMaxRing];
   __shared__ __align__(8) uint64_t w_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_stat[2][2][16];  // [epilogue group][double buffer][8 groups x (sum, sumsq)]
+  __shared__ float s_stat[NG][2][16];  // [epilogue group][double buffer][8 groups x (sum, sumsq)]
   __shared__ float s_bias[COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,8 +114,16 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
   }
-  if (threadIdx.x < 64) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
+  if (threadIdx.x < NG * 32) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
   for (int c = threadIdx.x; c < COUT; c += kMThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+  if (p.merged) {
+    // the input has 8 channels but K = 16 per MMA: the second chunk of every stage is zeroed once and never loaded
+    for (int s = 0; s < p.stages; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(smem + (p_addr - w_addr) + size_t(s) * plane_bytes + kMChunkBytes);
+      for (int i = threadIdx.x; i < kMChunkBytes / 16; i += kMThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+  }
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
@@ -124,7 +139,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       int stage = 0;
       uint32_t phase = 0;
       int w_n = -1;  // sample whose weights are resident (per-sample weights: folded EvoNorm affine)
-      const uint32_t tx = uint32_t(p.kc) * kMChunkData;
+      const uint32_t tx = p.merged ? uint32_t(kMChunkData) : uint32_t(p.kc) * kMChunkData;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const MarchItem it = decode_item(p, item);
         if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
@@ -153,8 +168,14 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
           } else {
             const uint32_t dst = p_addr + uint32_t(stage) * plane_bytes;
             mbar_expect_tx_a(fb, tx);
-            for (int c = 0; c < p.kc; ++c)
-              tma_load_5d_a(dst + c * kMChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
+            if (p.merged) {
+              // one box of 18 rows x 160 B (10 voxels x 8 channels, contiguous in HBM) instead of 180 rows x 16 B:
+              // the TMA engine is request-rate bound on 16 B rows (2000 cycles per plane against 650 of MMAs)
+              tma_load_5d_a(dst, &tmX, fb, (it.w0 - 1) * 8, it.h0 - 1, dz, it.n, 0);
+            } else {
+              for (int c = 0; c < p.kc; ++c)
+                tma_load_5d_a(dst + c * kMChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -293,7 +314,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
       __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy);
       const size_t ystep = size_t(p.H) * p.W * p.ldy;
       for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
-        if (int((plane_cnt++) & 1u) != grp) {  // the other group's plane: only advance the ring cursor
+        if (int((plane_cnt++) % uint32_t(NG)) != grp) {  // another group's plane: only advance the ring cursor
           use_par ^= 1u << r;
           r = r + 1 == RING ? 0 : r + 1;
           continue;
@@ -301,78 +322,89 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
         mbar_wait_a(accf0 + 8u * r, (use_par >> r) & 1u);
         use_par ^= 1u << r;
         tc_fence_after();
-        float v[COUT];
-        if (!(p.variant & 64)) {
-#pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 16) tmem_ld16(tlane + r * COUT + uint32_t(c0), v + c0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16_zero(tlane + r * COUT + uint32_t(c0));
-          tmem_st_wait();
-        } else {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] = 0.f;
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(acce0 + 8u * r);  // slot drained + zeroed: the MMA warp may reuse it
+        const uint32_t tcol = tlane + r * COUT;
+        const uint32_t acce_r = acce0 + 8u * r;
         r = r + 1 == RING ? 0 : r + 1;
-        if (p.variant & 32) continue;  // debug: handshake only
-        if (trow && valid) {  // folded input affine: the bias depends on the border class of the output voxel
-          const float4* tb = reinterpret_cast<const float4*>(trow + size_t(border_class(it.d0 + so, p.D)) * 9 * COUT);
-#pragma unroll
-          for (int c4 = 0; c4 < COUT / 4; ++c4) {
-            const float4 t4 = __ldg(tb + c4);
-            v[c4 * 4 + 0] += t4.x; v[c4 * 4 + 1] += t4.y; v[c4 * 4 + 2] += t4.z; v[c4 * 4 + 3] += t4.w;
-          }
-        } else if (!trow) {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] += s_bias[c];
-        }
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-          const float val = v[c];
-          const float sv = valid ? val : 0.f;
-          gs[c / GS] += sv;
-          gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
-        }
-        if (p.ex.act) {  // one branch around the whole unrolled loop: the 48 ex2/rcp chains interleave
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] = swishf(v[c]);
-        }
+        const float* tb = (trow && valid) ? trow + size_t(border_class(it.d0 + so, p.D)) * 9 * COUT : nullptr;
         uint4 o[COUT / 8];
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 8) {
-          o[c0 / 8].x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
-          o[c0 / 8].y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
-          o[c0 / 8].z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
-          o[c0 / 8].w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
-        }
-        if (valid && !(p.variant & 8)) {
+        for (int c0 = 0; c0 < COUT; c0 += PC) {
+          float v[PC];
+          if (!(p.variant & 64)) {
 #pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 8) *reinterpret_cast<uint4*>(yrow + c0) = o[c0 / 8];
-        }
-        if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
+            for (int c = 0; c < PC; c += 16) tmem_ld16(tcol + uint32_t(c0 + c), v + c);
+            tmem_ld_wait();
 #pragma unroll
-          for (int b = 0; b < NCS; ++b) {
-            float t[32];
+            for (int c = 0; c < PC; c += 16) tmem_st16_zero(tcol + uint32_t(c0 + c));
+          } else {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int c = b * 32 + i;
-              float2 f = make_float2(0.f, 0.f);
-              if (c < COUT) {
-                const uint4& q = o[c / 8];
-                const uint32_t wd = ((c % 8) / 2) == 0 ? q.x : (((c % 8) / 2) == 1 ? q.y : (((c % 8) / 2) == 2 ? q.z : q.w));
-                f = unpack_bf16x2(wd);
-              }
-              t[i] = valid ? f.x : 0.f;
-              t[i + 1] = valid ? f.y : 0.f;
+            for (int c = 0; c < PC; ++c) v[c] = 0.f;
+          }
+          if (c0 + PC >= COUT) {  // last pass: the slot is drained and zeroed, the MMA warp may reuse it
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(acce_r);
+          }
+          if (p.variant & 32) continue;  // debug: handshake only
+          if (tb) {  // folded input affine: the bias depends on the border class of the output voxel
+            const float4* t4p = reinterpret_cast<const float4*>(tb + c0);
+#pragma unroll
+            for (int c4 = 0; c4 < PC / 4; ++c4) {
+              const float4 t4 = __ldg(t4p + c4);
+              v[c4 * 4 + 0] += t4.x; v[c4 * 4 + 1] += t4.y; v[c4 * 4 + 2] += t4.z; v[c4 * 4 + 3] += t4.w;
             }
-            csum[b] += warp_transpose_sum32(t, lane);
+          } else if (!trow) {
+#pragma unroll
+            for (int c = 0; c < PC; ++c) v[c] += s_bias[c0 + c];
+          }
+#pragma unroll
+          for (int c = 0; c < PC; ++c) {
+            const float sv = valid ? v[c] : 0.f;
+            gs[(c0 + c) / GS] += sv;
+            gq[(c0 + c) / GS] = fmaf(sv, sv, gq[(c0 + c) / GS]);
+          }
+          if (p.ex.act == 1) {  // one branch around the whole unrolled loop: the ex2/rcp chains interleave
+#pragma unroll
+            for (int c = 0; c < PC; ++c) v[c] = swishf(v[c]);
+          } else if (p.ex.act == 2) {
+#pragma unroll
+            for (int c = 0; c < PC; ++c) v[c] = swishf_tanh(v[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < PC; c += 8) {
+            uint4& q = o[(c0 + c) / 8];
+            q.x = pack_bf16x2(v[c + 0], v[c + 1]);
+            q.y = pack_bf16x2(v[c + 2], v[c + 3]);
+            q.z = pack_bf16x2(v[c + 4], v[c + 5]);
+            q.w = pack_bf16x2(v[c + 6], v[c + 7]);
+            if (valid && !(p.variant & 8)) *reinterpret_cast<uint4*>(yrow + c0 + c) = q;
+          }
+        }
+        if (p.variant & 32) continue;
+        if constexpr (PC == COUT) {
+          if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
+#pragma unroll
+            for (int b = 0; b < NCS; ++b) {
+              float t[32];
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const int c = b * 32 + i;
+                float2 f = make_float2(0.f, 0.f);
+                if (c < COUT) {
+                  const uint4& q = o[c / 8];
+                  const uint32_t wd = ((c % 8) / 2) == 0 ? q.x : (((c % 8) / 2) == 1 ? q.y : (((c % 8) / 2) == 2 ? q.z : q.w));
+                  f = unpack_bf16x2(wd);
+                }
+                t[i] = valid ? f.x : 0.f;
+                t[i + 1] = valid ? f.y : 0.f;
+              }
+              csum[b] += warp_transpose_sum32(t, lane);
+            }
           }
         }
       }
-      if (p.ex.chan_sum) {
+      if (PC == COUT && p.ex.chan_sum) {
 #pragma unroll
         for (int b = 0; b < NCS; ++b)
           if (b * 32 + lane < COUT) atomicAdd(p.ex.chan_sum + size_t(it.n) * COUT + b * 32 + lane, csum[b]);
@@ -386,8 +418,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
             atomicAdd(&s_stat[grp][buf][g * 2 + 1], b);
           }
         }
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // the four warps of this epilogue group only
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");  // the four warps of this epilogue group only
         if (quad == 2 && lane < 16) {  // warp 2 / warp 6
           const float sv = s_stat[grp][buf][lane];
           s_stat[grp][buf][lane] = 0.f;
@@ -496,18 +527,26 @@ extern "C" int b21_pack_conv_weight_march_fold(const float* w, void* packed, int
   return B21_OK;
 }
 
-template <int COUT>
-static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
-                        cudaStream_t stream) {
+template <int COUT, int NG>
+static int launch_march_ng(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
+                           cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMSmemBudget));
     attr_set = true;
   }
-  conv_march_kernel<COUT><<<grid, kMThreads, smem_bytes, stream>>>(tm, p);
+  conv_march_kernel<COUT, NG><<<grid, kMThreadsBase + NG * 128, smem_bytes, stream>>>(tm, p);
   B21_LAUNCH_CHECK("conv_march_kernel");
   return B21_OK;
+}
+
+template <int COUT>
+static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
+                        cudaStream_t stream) {
+  // epilogue-bound input conv (one real 8-channel chunk, no SE channel sums): four epilogue groups
+  if (p.merged && !p.ex.chan_sum && !(p.variant & 128)) return launch_march_ng<COUT, 4>(tm, p, smem_bytes, grid, stream);
+  return launch_march_ng<COUT, 2>(tm, p, smem_bytes, grid, stream);
 }
 
 static int march_fwd_impl(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
@@ -587,7 +626,15 @@ static int march_fwd_impl(const void* x, int ldx, const void* w_march, const flo
   const int grid = p.items < sms ? p.items : sms;
 
   CUtensorMap tm;
-  {
+  p.merged = (cin == 8 && ldx == 8) ? 1 : 0;
+  if (p.merged) {
+    const uint64_t dims[5] = {(uint64_t)w * 8, (uint64_t)h, (uint64_t)d, (uint64_t)n, 1};
+    const uint64_t str[4] = {uint64_t(w) * 16, uint64_t(h) * w * 16, uint64_t(d) * h * w * 16,
+                             uint64_t(n) * d * h * w * 16};
+    const uint32_t box[5] = {8 * (uint32_t)kMHW, (uint32_t)kMHH, 1, 1, 1};
+    int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  } else {
     const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
     const uint64_t str[4] = {uint64_t(ldx) * 2, uint64_t(w) * ldx * 2, uint64_t(h) * w * ldx * 2,
                              uint64_t(d) * h * w * ldx * 2};

@@ -14,14 +14,17 @@
 //   * GroupNorm/EvoNorm group statistics are accumulated in registers across all tiles of a sample and flushed
 //     with one round of double atomics per CTA.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 and 6..9 = two epilogue groups:
+// group g drains accumulator buffer g (tiles with it % 2 == g), so that one group's tcgen05.ld / MUFU / store
+// latency chain overlaps the other's (a single group left the SM idle for half of every tile: 1570 cycles per tile
+// against 810 cycles of HBM time at 48 -> 24).
 #include "ptx.cuh"
 #include "fold.cuh"
 #include "host_common.h"
 
 namespace b21 {
 
-constexpr int kPtThreads = 192;
+constexpr int kPtThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9: two epilogue groups (alternate tiles)
 constexpr int kPtABytes = 128 * 128;  // one stage: 128 voxels x 64 bf16
 constexpr int kPtMaxStages = 8;
 constexpr int kPtSmemBudget = 200 * 1024;
@@ -161,6 +164,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const int quad = warp & 3;
+    const uint32_t grp = uint32_t(warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
     float gs[8], gq[8];
@@ -183,6 +187,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     uint32_t it = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      if ((it & 1u) != grp) continue;  // the other group's tile (and accumulator buffer)
       const int n = tile / p.tiles_per_n;
       const long long r = (long long)(tile - n * p.tiles_per_n) * 128 + row;
       const bool valid = r < p.nvox;

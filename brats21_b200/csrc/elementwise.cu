@@ -131,27 +131,46 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
 
 // ------------------------------------------------------------------------------------------ SE gate
 // one block per n: scale[n][c] = 1 + sigmoid(W2 relu(W1 m + b1) + b2), m = chan_sum * inv_count
-__global__ void se_gate_kernel(const float* __restrict__ chan_sum, const float* __restrict__ w1,
-                               const float* __restrict__ b1, const float* __restrict__ w2,
-                               const float* __restrict__ b2, float* __restrict__ scale, int C, int Hd,
-                               float inv_count) {
+__global__ void __launch_bounds__(1024) se_gate_kernel(const float* __restrict__ chan_sum, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ scale, int C,
+                                                       int Hd, float inv_count) {
   extern __shared__ float sm[];  // m[C], hid[Hd]
   float* m = sm;
   float* hid = sm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) m[c] = chan_sum[size_t(n) * C + c] * inv_count;
   __syncthreads();
+  // latency-bound (4 CTAs, two dependent mat-vecs): 32 warps, every lane keeps up to 12 independent loads in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int j = warp; j < Hd; j += nw) {
+    const float* wr = w1 + size_t(j) * C;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += w1[size_t(j) * C + c] * m[c];
+    int c = lane;
+    for (; c + 352 < C; c += 384) {
+      float t[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) t[k] = __ldg(wr + c + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) s = fmaf(t[k], m[c + 32 * k], s);
+    }
+    for (; c < C; c += 32) s = fmaf(__ldg(wr + c), m[c], s);
     s = warp_sum(s);
     if (lane == 0) hid[j] = fmaxf(s + b1[j], 0.f);
   }
   __syncthreads();
   for (int c = warp; c < C; c += nw) {
+    const float* wr = w2 + size_t(c) * Hd;
     float s = 0.f;
-    for (int j = lane; j < Hd; j += 32) s += w2[size_t(c) * Hd + j] * hid[j];
+    int j = lane;
+    for (; j + 160 < Hd; j += 192) {
+      float t[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) t[k] = __ldg(wr + j + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fmaf(t[k], hid[j + 32 * k], s);
+    }
+    for (; j < Hd; j += 32) s = fmaf(__ldg(wr + j), hid[j], s);
     s = warp_sum(s);
     if (lane == 0) scale[size_t(n) * C + c] = 1.f + 1.f / (1.f + expf(-(s + b2[c])));
   }
@@ -479,7 +498,7 @@ extern "C" int b21_se_gate(const float* chan_sum, const float* w1, const float* 
                            float* scale, int n, int c, int hidden, float inv_count, void* stream) {
   B21_CHECK_ARG(chan_sum && w1 && b1 && w2 && b2 && scale, "se_gate: null pointer");
   B21_CHECK_ARG(n > 0 && c > 0 && hidden > 0, "se_gate: bad sizes");
-  se_gate_kernel<<<n, 256, sizeof(float) * (c + hidden), (cudaStream_t)stream>>>(chan_sum, w1, b1, w2, b2, scale, c, hidden, inv_count);
+  se_gate_kernel<<<n, 1024, sizeof(float) * (c + hidden), (cudaStream_t)stream>>>(chan_sum, w1, b1, w2, b2, scale, c, hidden, inv_count);
   B21_LAUNCH_CHECK("se_gate_kernel");
   return B21_OK;
 }

@@ -8,7 +8,8 @@ struct FoldExtras {
   const float* table;   // bias table [N][ncls][Cout] fp32 (ncls = 27 border classes for k = 3, 1 for k = 1); replaces bias
   float* chan_sum;      // [N][Cout] fp32: per-channel sums of the STORED (bf16-rounded) outputs (SE squeeze), or NULL
   long long wstride;    // bytes between the per-sample packed weights (0 = one shared weight set)
-  int act;              // 0 = identity, 1 = x * sigmoid(x) applied before the store (after bias and statistics)
+  int act;              // 0 = identity, 1 = x * sigmoid(x) applied before the store (after bias and statistics),
+                        // 2 = the same through ONE MUFU op (tanh.approx): for epilogue-bound layers (Cin = 8)
 };
 
 __device__ __forceinline__ int border_class(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
@@ -19,6 +20,17 @@ __device__ __forceinline__ float swishf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return x * r;
+}
+
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op instead of two.  tanh.approx.f32 has a maximum relative
+// error of 2^-11, i.e. |error| <= 2.5e-4 * |x|: below the bf16 rounding of the stored value for x > 0 and about one
+// bf16 ulp on the negative tail.  Used where the MUFU pipe, not the tensor pipe, bounds the kernel (the 8 -> 48 input
+// conv: 96 MUFU ops per voxel against 9 MMAs per 128 voxels).
+__device__ __forceinline__ float swishf_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
 }
 
 // Transposed warp reduction: every lane holds 32 values v[0..32); afterwards v[0] of lane l is the sum over all

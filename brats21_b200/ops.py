@@ -171,8 +171,11 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
     else:
         assert h >= 8 and w >= 8
         name = "b21_conv3d_march_fwd_fold" if pw.w_march is not None else "b21_conv3d_slide_fwd_fold"
+        act_code = int(act)
+        if act and pw.w_march is not None and cin <= 8 and fast_input_swish:
+            act_code = 2  # input conv: 9 MMAs per plane, the epilogue's MUFU work is the bound (fold.cuh: swishf_tanh)
         call(name, ptr(x), _ld(x), ptr(wts), wstride, ptr(pw.bias), ptr(table), ptr(out), _ld(out), ptr(stats),
-             ptr(chan_sum), int(act), n, d, h, w, cin, pw.cout, stream_ptr())
+             ptr(chan_sum), act_code, n, d, h, w, cin, pw.cout, stream_ptr())
     if prof is not None:
         e1.record()
         kind = "point" if pw.taps == 1 else ("march" if pw.w_march is not None else "slide")
@@ -198,6 +201,8 @@ use_march = True
 use_slide = True
 # folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations
 use_fold = True
+# single-MUFU swish (tanh.approx) in the epilogue of the Cin = 8 input conv of the folded path; tests flip it
+fast_input_swish = True
 # replay the inference forward of a window batch from a CUDA graph (networks._B21Net.forward_infer)
 use_graphs = True
 # plane-marching weight gradient (conv_wgrad_march.cu) for the k = 3 layers with cin <= 96
