@@ -45,6 +45,8 @@ _SIGNATURES = {
     "b21_pack_conv_weight_march_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b21_pack_conv_weight_slide_fold": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b21_conv3d_march_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_conv3d_march_fwd_fold2": [_vp, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i,
+                                   _vp],
     "b21_conv3d_slide_fwd_fold": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv1x1_fwd_fold": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp],
     "b21_affine_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],

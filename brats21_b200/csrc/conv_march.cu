@@ -52,6 +52,7 @@ struct ConvMarchParams {
   int stages, ring;
   uint32_t wbytes;
   FoldExtras ex;
+  int split;    // 8-channel chunks [split, kc) come from a SECOND tensor (tmX2): channel concat without a concat buffer
   int merged;   // Cin == 8 dense input (ld = 8): (w, c) merged into one tensor-map dimension, chunk 1 is zero in smem
   int variant;  // debug (B21_MARCH_VARIANT): bit2 no TMA loads, bit3 no stores, bit4 three taps only, bit5 no epilogue math/stores, bit6 no TMEM ld/st
 };
@@ -77,9 +78,14 @@ __device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int i
   return it;
 }
 
-template <int COUT, int NG>
+// KS = compile-time number of 16-channel k-steps (0: runtime loop).  With a runtime count the compiler emits a
+// branchy remainder loop around every tcgen05.mma (about 80 cycles of issue per MMA against 72 of execution at
+// N = 144, so the tensor pipe drains during the per-plane bookkeeping); fully unrolled, an MMA costs two uniform
+// 64-bit adds and the issue thread runs ahead of the pipe.
+template <int COUT, int NG, int KS>
 __global__ void __launch_bounds__(kMThreadsBase + NG * 128, 1)
-conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams p) {
+conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
+                  const ConvMarchParams p) {
   constexpr int kMThreads = kMThreadsBase + NG * 128;
   constexpr int PC = NG > 2 ? 16 : COUT;  // columns per epilogue pass
   constexpr uint32_t RING = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;  // accumulator slots in TMEM
@@ -113,6 +119,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
     mbar_init(&w_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmX2);
   }
   if (threadIdx.x < NG * 32) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
   for (int c = threadIdx.x; c < COUT; c += kMThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
@@ -173,8 +180,10 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
               // the TMA engine is request-rate bound on 16 B rows (2000 cycles per plane against 650 of MMAs)
               tma_load_5d_a(dst, &tmX, fb, (it.w0 - 1) * 8, it.h0 - 1, dz, it.n, 0);
             } else {
-              for (int c = 0; c < p.kc; ++c)
+              for (int c = 0; c < p.split; ++c)
                 tma_load_5d_a(dst + c * kMChunkBytes, &tmX, fb, c * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
+              for (int c = p.split; c < p.kc; ++c)
+                tma_load_5d_a(dst + c * kMChunkBytes, &tmX2, fb, (c - p.split) * 8, it.w0 - 1, it.h0 - 1, dz, it.n);
             }
           }
           if (++stage == p.stages) {
@@ -240,7 +249,40 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
           const uint32_t id1 = len1 == 2 ? idesc2 : idesc1;
           uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
           uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
-          if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
+          if constexpr (KS > 0) {
+            constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
+            if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                if (kh < nkh) {
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+                      umma_bf16(col0, a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep,
+                                bq + uint64_t((kh * 3 + kw) * KS + ks) * kBStep, id0, 1u);
+                  }
+                }
+              }
+            } else {
+              const uint64_t b1 = uint64_t(len0) * COUT;
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                if (kh < nkh) {
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                      const uint64_t ad = a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep;
+                      const uint64_t bd = bq + uint64_t((kh * 3 + kw) * KS + ks) * kBStep;
+                      umma_bf16(col0, ad, bd, id0, 1u);
+                      umma_bf16(col1, ad, bd + b1, id1, 1u);
+                    }
+                  }
+                }
+              }
+            }
+          } else if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
             for (int kh = 0; kh < nkh; ++kh, a_row += kMHW) {
               uint64_t a_tap = a_row;
               for (int kw = 0; kw < 3; ++kw, ++a_tap) {
@@ -261,7 +303,8 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const ConvMarchParams
               }
             }
           }
-          umma_commit_a(empty0 + 8u * stage);
+          if (p.variant & 512) mbar_arrive_a(empty0 + 8u * stage);  // debug (only with bit2): one commit less per plane
+          else umma_commit_a(empty0 + 8u * stage);
           if (i >= 2) umma_commit_a(accf0 + 8u * r_lo);  // output plane so = i - 1 is complete
           if (i == it.Lc && it.d0 + it.Lc >= p.D) {       // no plane i + 1 exists: so = i is complete as well
             uint32_t r = r_lo + uint32_t(1 - jlo);
@@ -527,31 +570,37 @@ extern "C" int b21_pack_conv_weight_march_fold(const float* w, void* packed, int
   return B21_OK;
 }
 
-template <int COUT, int NG>
-static int launch_march_ng(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
-                           cudaStream_t stream) {
+template <int COUT, int NG, int KS>
+static int launch_march_ng(const CUtensorMap& tm, const CUtensorMap& tm2, const ConvMarchParams& p, size_t smem_bytes,
+                           int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT, NG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMSmemBudget));
     attr_set = true;
   }
-  conv_march_kernel<COUT, NG><<<grid, kMThreadsBase + NG * 128, smem_bytes, stream>>>(tm, p);
+  conv_march_kernel<COUT, NG, KS><<<grid, kMThreadsBase + NG * 128, smem_bytes, stream>>>(tm, tm2, p);
   B21_LAUNCH_CHECK("conv_march_kernel");
   return B21_OK;
 }
 
 template <int COUT>
-static int launch_march(const CUtensorMap& tm, const ConvMarchParams& p, size_t smem_bytes, int grid,
-                        cudaStream_t stream) {
+static int launch_march(const CUtensorMap& tm, const CUtensorMap& tm2, const ConvMarchParams& p, size_t smem_bytes,
+                        int grid, cudaStream_t stream) {
+  const int ks = (p.variant & 256) ? 0 : p.kc >> 1;
   // epilogue-bound input conv (one real 8-channel chunk, no SE channel sums): four epilogue groups
-  if (p.merged && !p.ex.chan_sum && !(p.variant & 128)) return launch_march_ng<COUT, 4>(tm, p, smem_bytes, grid, stream);
-  return launch_march_ng<COUT, 2>(tm, p, smem_bytes, grid, stream);
+  if (p.merged && !p.ex.chan_sum && !(p.variant & 128)) return launch_march_ng<COUT, 4, 1>(tm, tm2, p, smem_bytes, grid, stream);
+  switch (ks) {
+    case 1: return launch_march_ng<COUT, 2, 1>(tm, tm2, p, smem_bytes, grid, stream);
+    case 2: return launch_march_ng<COUT, 2, 2>(tm, tm2, p, smem_bytes, grid, stream);
+    case 3: return launch_march_ng<COUT, 2, 3>(tm, tm2, p, smem_bytes, grid, stream);
+    default: return launch_march_ng<COUT, 2, 0>(tm, tm2, p, smem_bytes, grid, stream);
+  }
 }
 
 static int march_fwd_impl(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                           double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
-                          void* stream_);
+                          void* stream_, const void* x2 = nullptr, int ldx2 = 0, int cin1 = 0);
 
 extern "C" int b21_conv3d_march_fwd(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                                     double* stats, int n, int d, int h, int w, int cin, int cout, void* stream_) {
@@ -571,14 +620,35 @@ extern "C" int b21_conv3d_march_fwd_fold(const void* x, int ldx, const void* w_m
   return march_fwd_impl(x, ldx, w_march, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_);
 }
 
+// Same with the input channels split over TWO tensors (x: channels [0, cin1), x2: channels [cin1, cin)): the consumer
+// of a channel concat (equiunet2021.py:310,315,319) reads both producers' DENSE outputs, so neither producer writes a
+// 48-byte half of a 96-byte record (partial-sector writes cost 1.3x the DRAM traffic, profiles/r01h_point_full.md).
+extern "C" int b21_conv3d_march_fwd_fold2(const void* x, int ldx, int cin1, const void* x2, int ldx2,
+                                          const void* w_march, long long wstride_n, const float* bias,
+                                          const float* bias_table, void* y, int ldy, double* stats, float* chan_sum,
+                                          int act, int n, int d, int h, int w, int cin, int cout, void* stream_) {
+  B21_CHECK_ARG(x2, "conv3d_march_fwd_fold2: null second input");
+  B21_CHECK_ARG(!bias_table || (d >= 2 && h >= 2 && w >= 2), "conv3d_march_fwd_fold2: border classes need dims >= 2");
+  B21_CHECK_ARG(wstride_n >= 0 && wstride_n % 16 == 0, "conv3d_march_fwd_fold2: weight stride must be a multiple of 16 B");
+  FoldExtras ex = {bias_table, chan_sum, wstride_n, act};
+  return march_fwd_impl(x, ldx, w_march, bias, y, ldy, stats, n, d, h, w, cin, cout, ex, stream_, x2, ldx2, cin1);
+}
+
 static int march_fwd_impl(const void* x, int ldx, const void* w_march, const float* bias, void* y, int ldy,
                           double* stats, int n, int d, int h, int w, int cin, int cout, const FoldExtras& ex,
-                          void* stream_) {
+                          void* stream_, const void* x2, int ldx2, int cin1) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (x2) {
+    B21_CHECK_ARG(cin1 > 0 && cin1 < cin && cin1 % 8 == 0 && (cin - cin1) % 8 == 0 && ldx >= cin1 &&
+                      ldx2 >= cin - cin1 && ldx2 % 8 == 0 && (reinterpret_cast<uintptr_t>(x2) & 15) == 0,
+                  "conv3d_march_fwd: bad split input (cin %d = %d + %d, ld %d / %d)", cin, cin1, cin - cin1, ldx, ldx2);
+  } else {
+    cin1 = cin;
+  }
   B21_CHECK_ARG(x && w_march && y, "conv3d_march_fwd: null pointer");
   B21_CHECK_ARG(n > 0 && d > 0 && h > 0 && w > 0, "conv3d_march_fwd: bad shape %d %d %d %d", n, d, h, w);
   B21_CHECK_ARG(b21_conv_march_supported(cin, cout), "conv3d_march_fwd: (cin %d, cout %d) unsupported", cin, cout);
-  B21_CHECK_ARG(ldx >= cin && ldx % 8 == 0 && ldy >= cout && ldy % 8 == 0, "conv3d_march_fwd: bad ldx %d / ldy %d", ldx, ldy);
+  B21_CHECK_ARG(ldx >= cin1 && ldx % 8 == 0 && ldy >= cout && ldy % 8 == 0, "conv3d_march_fwd: bad ldx %d / ldy %d", ldx, ldy);
   B21_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(w_march) & 15) == 0,
                 "conv3d_march_fwd: pointers must be 16-byte aligned");
@@ -625,8 +695,9 @@ static int march_fwd_impl(const void* x, int ldx, const void* w_march, const flo
   p.items = int(tiles * p.segs);
   const int grid = p.items < sms ? p.items : sms;
 
-  CUtensorMap tm;
-  p.merged = (cin == 8 && ldx == 8) ? 1 : 0;
+  CUtensorMap tm, tm2;
+  p.split = x2 ? cin1 / 8 : p.kc;
+  p.merged = (cin == 8 && ldx == 8 && !x2) ? 1 : 0;
   if (p.merged) {
     const uint64_t dims[5] = {(uint64_t)w * 8, (uint64_t)h, (uint64_t)d, (uint64_t)n, 1};
     const uint64_t str[4] = {uint64_t(w) * 16, uint64_t(h) * w * 16, uint64_t(d) * h * w * 16,
@@ -635,19 +706,28 @@ static int march_fwd_impl(const void* x, int ldx, const void* w_march, const flo
     int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   } else {
-    const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t dims[5] = {(uint64_t)cin1, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
     const uint64_t str[4] = {uint64_t(ldx) * 2, uint64_t(w) * ldx * 2, uint64_t(h) * w * ldx * 2,
                              uint64_t(d) * h * w * ldx * 2};
     const uint32_t box[5] = {8, (uint32_t)kMHW, (uint32_t)kMHH, 1, 1};
     int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   }
+  tm2 = tm;
+  if (x2) {
+    const uint64_t dims[5] = {(uint64_t)(cin - cin1), (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t str[4] = {uint64_t(ldx2) * 2, uint64_t(w) * ldx2 * 2, uint64_t(h) * w * ldx2 * 2,
+                             uint64_t(d) * h * w * ldx2 * 2};
+    const uint32_t box[5] = {8, (uint32_t)kMHW, (uint32_t)kMHH, 1, 1};
+    int r = encode_tmap_bf16(&tm2, x2, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
   if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
   const size_t smem_bytes = ((size_t(p.wbytes) + 127) & ~size_t(127)) + size_t(p.stages) * p.kc * kMChunkBytes + 128;
   switch (cout) {
-    case 16: return launch_march<16>(tm, p, smem_bytes, grid, stream);
-    case 32: return launch_march<32>(tm, p, smem_bytes, grid, stream);
-    case 48: return launch_march<48>(tm, p, smem_bytes, grid, stream);
-    default: return launch_march<64>(tm, p, smem_bytes, grid, stream);
+    case 16: return launch_march<16>(tm, tm2, p, smem_bytes, grid, stream);
+    case 32: return launch_march<32>(tm, tm2, p, smem_bytes, grid, stream);
+    case 48: return launch_march<48>(tm, tm2, p, smem_bytes, grid, stream);
+    default: return launch_march<64>(tm, tm2, p, smem_bytes, grid, stream);
   }
 }

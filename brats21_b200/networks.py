@@ -482,7 +482,7 @@ class EquiUnetASSPEvo(_B21Net):
         t1, t2, t3, t4 = B("t1", 1, f[0]), B("t2", 2, f[1]), B("t3", 4, f[2]), B("t4", 8, f[3])
         d1, d2, d3, d4 = B("d1", 1, f[0]), B("d2", 2, f[1]), B("d3", 4, f[2]), B("d4", 8, f[3])
         p1, p2, p3 = B("p1", 2, 2 * f[0]), B("p2", 4, 2 * f[1]), B("p3", 8, 2 * f[2])
-        cat1, cat2, cat3 = B("cat1", 1, f[0]), B("cat2", 2, f[1]), B("cat3", 4, f[2])
+        cat1, cat2, cat3 = None, B("cat2", 2, f[1]), B("cat3", 4, f[2])
         ab_t1, ab_t2 = self._ab(ws, "ab_t1", n, f[0]), self._ab(ws, "ab_t2", n, f[1])
         ab_d1, ab_d2 = self._ab(ws, "ab_d1", n, f[0]), self._ab(ws, "ab_d2", n, f[1])
         ab_c1, ab_c2 = self._ab(ws, "ab_c1", n, f[0]), self._ab(ws, "ab_c2", n, f[1])
@@ -506,7 +506,15 @@ class EquiUnetASSPEvo(_B21Net):
             ops.conv3d(d4, pk[f"aspp.convs.{i}"], out=acat[..., i * q:(i + 1) * q], dil=dil)
         assp = self._convevo("aspp.conv_k1", acat, t4, stats)
 
-        self._fconvevo("bridge1", d1, ab_d1, cat1[..., :h0], stats, (ab_c1[0][:, :h0], ab_c1[1][:, :h0]))
+        # level-1 concat [bridge1 | up(upconv1)]: two DENSE 24-channel tensors read side by side by decoder1's first
+        # conv (a 48-byte half of a 96-byte record is a partial-sector write: 1.3x the DRAM traffic on both producers)
+        split1 = ops.split_concat and self._packed["decoder1.c0"].w_march is not None
+        if split1:
+            cat1a, cat1b = B("cat1a", 1, h0), B("cat1b", 1, h0)
+        else:
+            cat1 = B("cat1", 1, f[0])
+            cat1a, cat1b = cat1[..., :h0], cat1[..., h0:]
+        self._fconvevo("bridge1", d1, ab_d1, cat1a, stats, (ab_c1[0][:, :h0], ab_c1[1][:, :h0]))
         self._fconvevo("bridge2", d2, ab_d2, cat2[..., :h1], stats, (ab_c2[0][:, :h1], ab_c2[1][:, :h1]))
         self._convevo("bridge3", d3, cat3[..., :f[2] // 2], stats)
 
@@ -521,9 +529,9 @@ class EquiUnetASSPEvo(_B21Net):
         self._fblock("decoder2", cat2, ab_c2, t2, up2, stats, cs[1], ab_t2, ab_u2)
         uc1 = B("uc1", 2, f[1] // 4)
         self._fconvevo("upconv1", up2, ab_u2, uc1, stats, (ab_c1[0][:, h0:], ab_c1[1][:, h0:]))
-        ops.upsample2x(uc1, cat1[..., h0:])
+        ops.upsample2x(uc1, cat1b)
         up1 = B("up1", 1, f[0])
-        self._fblock("decoder1", cat1, ab_c1, t1, up1, stats, cs[0], ab_t1, ab_u1)
+        self._fblock("decoder1", (cat1a, cat1b) if split1 else cat1, ab_c1, t1, up1, stats, cs[0], ab_t1, ab_u1)
         out = ops.head_conv(up1, pk["out_conv.w"], pk["out_conv.bias"], scale=ab_u1[0], offset=ab_u1[1])
         deeps: List[torch.Tensor] = []
         if want_deep and self.deep_supervision:

@@ -152,7 +152,14 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
     """conv3d whose INPUT is a stored swish tensor S with the affine ab = (A, B) [n, cin] folded into per-sample
     weights and a border-class bias table, and whose OUTPUT is stored as swish(conv + bias) (act) with the group
     statistics (and optionally the per-channel sums of the stored values, for the SE squeeze)."""
+    x2 = None
+    if isinstance(x, (tuple, list)):  # channel concat of two dense tensors, read in place by the march kernel
+        x, x2 = x
+        assert x2.shape[:4] == x.shape[:4] and x2.dtype == torch.bfloat16 and pw.w_march is not None
     n, d, h, w, cin = x.shape
+    cin1 = cin
+    if x2 is not None:
+        cin = cin1 + x2.shape[-1]
     assert x.dtype == torch.bfloat16 and cin == pw.cin and out.shape == (n, d, h, w, pw.cout)
     if ab is None:
         wts = pw.w if pw.taps == 1 else (pw.w_march if pw.w_march is not None else pw.w_slide)
@@ -174,8 +181,13 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
         act_code = int(act)
         if act and pw.w_march is not None and cin <= 8 and fast_input_swish:
             act_code = 2  # input conv: 9 MMAs per plane, the epilogue's MUFU work is the bound (fold.cuh: swishf_tanh)
-        call(name, ptr(x), _ld(x), ptr(wts), wstride, ptr(pw.bias), ptr(table), ptr(out), _ld(out), ptr(stats),
-             ptr(chan_sum), act_code, n, d, h, w, cin, pw.cout, stream_ptr())
+        if x2 is not None:
+            call("b21_conv3d_march_fwd_fold2", ptr(x), _ld(x), cin1, ptr(x2), _ld(x2), ptr(wts), wstride, ptr(pw.bias),
+                 ptr(table), ptr(out), _ld(out), ptr(stats), ptr(chan_sum), act_code, n, d, h, w, cin, pw.cout,
+                 stream_ptr())
+        else:
+            call(name, ptr(x), _ld(x), ptr(wts), wstride, ptr(pw.bias), ptr(table), ptr(out), _ld(out), ptr(stats),
+                 ptr(chan_sum), act_code, n, d, h, w, cin, pw.cout, stream_ptr())
     if prof is not None:
         e1.record()
         kind = "point" if pw.taps == 1 else ("march" if pw.w_march is not None else "slide")
@@ -201,6 +213,8 @@ use_march = True
 use_slide = True
 # folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations
 use_fold = True
+# level-1 concat of the folded path as two dense tensors (b21_conv3d_march_fwd_fold2); tests flip it
+split_concat = True
 # single-MUFU swish (tanh.approx) in the epilogue of the Cin = 8 input conv of the folded path; tests flip it
 fast_input_swish = True
 # replay the inference forward of a window batch from a CUDA graph (networks._B21Net.forward_infer)

@@ -117,6 +117,12 @@ int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int cout, int 
 int b21_conv3d_march_fwd_fold(const void* x, int ldx, const void* w_march, long long wstride_n, const float* bias,
                               const float* bias_table, void* y, int ldy, double* stats, float* chan_sum, int act,
                               int n, int d, int h, int w, int cin, int cout, void* stream);
+/* b21_conv3d_march_fwd_fold with the input channels split over two tensors (x: [0, cin1), x2: [cin1, cin)): the
+ * consumer of a channel concat (torch.cat at equiunet2021.py:310,315,319) reads both producers' dense outputs. */
+int b21_conv3d_march_fwd_fold2(const void* x, int ldx, int cin1, const void* x2, int ldx2, const void* w_march,
+                               long long wstride_n, const float* bias, const float* bias_table, void* y, int ldy,
+                               double* stats, float* chan_sum, int act, int n, int d, int h, int w, int cin, int cout,
+                               void* stream);
 int b21_conv3d_slide_fwd_fold(const void* x, int ldx, const void* w_slide, long long wstride_n, const float* bias,
                               const float* bias_table, void* y, int ldy, double* stats, float* chan_sum, int act,
                               int n, int d, int h, int w, int cin, int cout, void* stream);

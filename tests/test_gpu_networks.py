@@ -123,3 +123,25 @@ def test_v2_folded_evonorm_path_matches_explicit_path(width, shape, n):
     for a, b in zip(deeps_f, ref_deeps):
         _check(a, b)
     assert ((out_f - out_e).norm() / out_e.norm()).item() <= 1.5e-2
+
+
+@pytest.mark.parametrize("width,shape,n", [(16, (16, 32, 48), 2), (48, (32, 48, 40), 1)])
+def test_v2_split_concat_matches_in_place_concat(width, shape, n):
+    """decoder1's first conv reading [bridge1 | up(upconv1)] as two dense tensors (b21_conv3d_march_fwd_fold2) is
+    the same arithmetic on the same values as reading one concat buffer.  The group statistics are accumulated with
+    atomics (order varies run to run), so the comparison is rel-L2 <= 1e-3 (a wrong channel mapping gives O(1))."""
+    from brats21_b200 import ops
+    from oracle import synth
+    net, _ = _build(2, width, 93)
+    x = torch.cat([synth.volume(seed=s, shape=shape) for s in range(n)]).to(DEV)
+    assert ops.split_concat
+    net._ensure_packed()
+    assert net._packed["decoder1.c0"].w_march is not None
+    out_s, _ = net(x)
+    ops.split_concat = False
+    try:
+        out_c, _ = net(x)
+    finally:
+        ops.split_concat = True
+    rel = ((out_s - out_c).norm() / out_c.norm()).item()
+    assert rel <= 1e-3, rel
