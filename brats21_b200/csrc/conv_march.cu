@@ -205,21 +205,50 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint64_t bd0 = dB + uint64_t(w_addr >> 4);
       const int ksteps = p.kc >> 1;
       const int nkh = (p.variant & 16) ? 1 : 3;
+      // The per-plane bookkeeping (ring / border arithmetic, slot claims, barrier waits: several hundred cycles of a
+      // single dependent instruction stream) used to sit between the last MMA of one plane and the first MMA of the
+      // next, and the tensor pipe — whose queue holds only a few MMAs — drained meanwhile (~760 idle cycles per plane,
+      // measured with the B21_MARCH_VARIANT switches).  It is now software-pipelined: the descriptor of the NEXT plane
+      // is computed and its barriers are awaited BETWEEN the kh groups of the current plane's MMAs.
+      struct PlaneDesc {
+        uint64_t a_row, bq;
+        uint32_t col0, id0, id1, b1;       // b1 = B-descriptor offset of the wrapped column groups (len1 > 0)
+        uint32_t sg_lo, r_lo, stage, phase;
+        int ngroups, len1, accf_lo, accf_hi;  // ring slots to commit after the MMAs (-1 = none)
+        bool need_w;
+      };
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0;
+      uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0, r_lo = 0;
       int w_n = -1;
       uint32_t w_par = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const MarchItem it = decode_item(p, item);
-        if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
-          w_n = it.n;
-          mbar_wait(&w_bar, w_par);
-          w_par ^= 1u;
-          tc_fence_after();
-        }
-        uint32_t r_lo = r_base;
-        for (int i = 0; i <= it.Lc + 1; ++i) {
+      int item = blockIdx.x, pi = 0;
+      bool have_item = false, pending_w = false;
+      MarchItem it;
+      it.n = it.h0 = it.w0 = it.d0 = it.Lc = 0;
+
+      // descriptor of the next valid input plane (pure arithmetic, no waits); false when this CTA's work is done
+      auto advance = [&](PlaneDesc& pd) -> bool {
+        for (;;) {
+          if (!have_item) {
+            if (item >= p.items) return false;
+            it = decode_item(p, item);
+            pi = 0;
+            r_lo = r_base;
+            have_item = true;
+            if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
+              w_n = it.n;
+              pending_w = true;
+            }
+          }
+          if (pi > it.Lc + 1) {
+            sg_base += uint32_t(it.Lc);
+            r_base = (r_base + uint32_t(it.Lc)) % RING;
+            item += gridDim.x;
+            have_item = false;
+            continue;
+          }
+          const int i = pi++;
           // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j; the lowest valid
           // group of plane i sits in ring slot r_lo, which advances by one per plane once i >= 3.
           if (i >= 3) r_lo = r_lo + 1 == RING ? 0 : r_lo + 1;
@@ -227,97 +256,116 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (dz < 0 || dz >= p.D) continue;
           const int jlo = i >= 2 ? 0 : 2 - i;
           const int jhi = i + 1 <= it.Lc ? 2 : it.Lc + 1 - i;
-          const int ngroups = jhi - jlo + 1;
-          const uint32_t sg_lo = sg_base + uint32_t(i + jlo - 2);
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const uint32_t sg = sg_lo + uint32_t(g);
-            if (g < ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
-              uint32_t r = r_lo + uint32_t(g);
-              r = r >= RING ? r - RING : r;
-              mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
-              claim_par ^= 1u << r;
-              next_fresh = sg + 1;
-            }
-          }
-          mbar_wait_a(full0 + 8u * stage, phase);
-          tc_fence_after();
+          pd.ngroups = jhi - jlo + 1;
+          pd.sg_lo = sg_base + uint32_t(i + jlo - 2);
+          pd.r_lo = r_lo;
           const int room = int(RING - r_lo);
-          const int len0 = ngroups < room ? ngroups : room, len1 = ngroups - len0;  // at most one ring wrap
-          const uint32_t col0 = tmem_base + r_lo * COUT, col1 = tmem_base;
-          const uint32_t id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
-          const uint32_t id1 = len1 == 2 ? idesc2 : idesc1;
-          uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
-          uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
-          if constexpr (KS > 0) {
-            constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
-            if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
-#pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                if (kh < nkh) {
-#pragma unroll
-                  for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-                      umma_bf16(col0, a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep,
-                                bq + uint64_t((kh * 3 + kw) * KS + ks) * kBStep, id0, 1u);
-                  }
-                }
-              }
-            } else {
-              const uint64_t b1 = uint64_t(len0) * COUT;
-#pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                if (kh < nkh) {
-#pragma unroll
-                  for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                      const uint64_t ad = a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep;
-                      const uint64_t bd = bq + uint64_t((kh * 3 + kw) * KS + ks) * kBStep;
-                      umma_bf16(col0, ad, bd, id0, 1u);
-                      umma_bf16(col1, ad, bd + b1, id1, 1u);
-                    }
-                  }
-                }
-              }
-            }
-          } else if (len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
-            for (int kh = 0; kh < nkh; ++kh, a_row += kMHW) {
-              uint64_t a_tap = a_row;
-              for (int kw = 0; kw < 3; ++kw, ++a_tap) {
-                uint64_t ad = a_tap;
-                for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) umma_bf16(col0, ad, bq, id0, 1u);
-              }
-            }
-          } else {
-            const uint64_t b1 = uint64_t(len0) * COUT;
-            for (int kh = 0; kh < nkh; ++kh, a_row += kMHW) {
-              uint64_t a_tap = a_row;
-              for (int kw = 0; kw < 3; ++kw, ++a_tap) {
-                uint64_t ad = a_tap;
-                for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
-                  umma_bf16(col0, ad, bq, id0, 1u);
-                  umma_bf16(col1, ad, bq + b1, id1, 1u);
-                }
-              }
-            }
-          }
-          if (p.variant & 512) mbar_arrive_a(empty0 + 8u * stage);  // debug (only with bit2): one commit less per plane
-          else umma_commit_a(empty0 + 8u * stage);
-          if (i >= 2) umma_commit_a(accf0 + 8u * r_lo);  // output plane so = i - 1 is complete
-          if (i == it.Lc && it.d0 + it.Lc >= p.D) {       // no plane i + 1 exists: so = i is complete as well
+          const int len0 = pd.ngroups < room ? pd.ngroups : room;  // at most one ring wrap
+          pd.len1 = pd.ngroups - len0;
+          pd.col0 = tmem_base + ((p.variant & 2048) ? 0u : r_lo * COUT);  // debug bit11: constant accumulator address
+          pd.id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
+          pd.id1 = pd.len1 == 2 ? idesc2 : idesc1;
+          pd.b1 = uint32_t(len0) * COUT;
+          pd.a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
+          pd.bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
+          pd.stage = uint32_t(stage);
+          pd.phase = phase;
+          pd.accf_lo = i >= 2 ? int(r_lo) : -1;  // output plane so = i - 1 is complete after this plane
+          pd.accf_hi = -1;
+          if (i == it.Lc && it.d0 + it.Lc >= p.D) {  // no plane i + 1 exists: so = i is complete as well
             uint32_t r = r_lo + uint32_t(1 - jlo);
-            r = r >= RING ? r - RING : r;
-            umma_commit_a(accf0 + 8u * r);
+            pd.accf_hi = int(r >= RING ? r - RING : r);
           }
+          pd.need_w = pending_w;
+          pending_w = false;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
+          return true;
         }
-        sg_base += uint32_t(it.Lc);
-        r_base = (r_base + uint32_t(it.Lc)) % RING;
+      };
+      // everything the plane's first MMA has to wait for
+      auto acquire = [&](const PlaneDesc& pd) {
+        if (pd.need_w) {
+          mbar_wait(&w_bar, w_par);
+          w_par ^= 1u;
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const uint32_t sg = pd.sg_lo + uint32_t(g);
+          if (g < pd.ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
+            uint32_t r = pd.r_lo + uint32_t(g);
+            r = r >= RING ? r - RING : r;
+            mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
+            claim_par ^= 1u << r;
+            next_fresh = sg + 1;
+          }
+        }
+        mbar_wait_a(full0 + 8u * pd.stage, pd.phase);
+        tc_fence_after();
+      };
+      // the MMAs of one kh row of taps
+      auto issue = [&](const PlaneDesc& pd, int kh) {
+        if (kh >= nkh) return;
+        if constexpr (KS > 0) {
+          constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
+          const uint64_t a0 = pd.a_row + uint64_t(kh * kMHW), b0 = pd.bq + uint64_t(kh * 3 * KS) * kBStep;
+          if (pd.len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks)
+                umma_bf16(pd.col0, a0 + uint64_t(kw) + uint64_t(ks) * kAStep, b0 + uint64_t(kw * KS + ks) * kBStep, pd.id0, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint64_t ad = a0 + uint64_t(kw) + uint64_t(ks) * kAStep;
+                const uint64_t bd = b0 + uint64_t(kw * KS + ks) * kBStep;
+                umma_bf16(pd.col0, ad, bd, pd.id0, 1u);
+                umma_bf16(tmem_base, ad, bd + pd.b1, pd.id1, 1u);
+              }
+            }
+          }
+        } else {
+          uint64_t a_tap = pd.a_row + uint64_t(kh * kMHW);
+          uint64_t bq = pd.bq + uint64_t(kh * 3 * ksteps) * b_step;
+          for (int kw = 0; kw < 3; ++kw, ++a_tap) {
+            uint64_t ad = a_tap;
+            for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
+              umma_bf16(pd.col0, ad, bq, pd.id0, 1u);
+              if (pd.len1 != 0) umma_bf16(tmem_base, ad, bq + pd.b1, pd.id1, 1u);
+            }
+          }
+        }
+      };
+      auto finish = [&](const PlaneDesc& pd) {
+        if (p.variant & 512) mbar_arrive_a(empty0 + 8u * pd.stage);  // debug (only with bit2): one commit less per plane
+        else umma_commit_a(empty0 + 8u * pd.stage);
+        if (pd.accf_lo >= 0) umma_commit_a(accf0 + 8u * uint32_t(pd.accf_lo));
+        if (pd.accf_hi >= 0) umma_commit_a(accf0 + 8u * uint32_t(pd.accf_hi));
+      };
+
+      PlaneDesc cur, nxt;
+      bool has = advance(cur);
+      if (has) acquire(cur);
+      while (has) {
+        issue(cur, 0);
+        const bool has_next = advance(nxt);
+        issue(cur, 1);
+        // new weights are loaded only after every MMA on the old ones has completed: that wait cannot be taken early
+        // (with a single k-step per tap the plane's MMAs are too short to cover the wait for the next plane's TMA)
+        const bool early = has_next && !nxt.need_w && KS != 1 && !(p.variant & 1024);
+        if (early) acquire(nxt);
+        issue(cur, 2);
+        finish(cur);
+        if (has_next && !early) acquire(nxt);
+        cur = nxt;
+        has = has_next;
       }
     }
   } else {
