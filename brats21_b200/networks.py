@@ -444,6 +444,8 @@ class EquiUnetASSPEvo(_B21Net):
     _FOLD_CONVS = ["encoder1.c0", "encoder1.c1", "encoder2.c0", "encoder2.c1", "decoder2.c0", "decoder2.c1",
                    "decoder1.c0", "decoder1.c1", "bridge1", "bridge2", "upconv1", "upconv2"]
 
+    _FOLD3_CONVS = ["encoder3.c0", "encoder3.c1", "decoder3.c0", "decoder3.c1", "bridge3"]
+
     def _fold_ok(self, d, h, w):
         return ops.use_fold and min(h, w) >= 16 and d >= 4 and all(ops.fold_supported(self._packed[k])
                                                                     for k in self._FOLD_CONVS)
@@ -494,9 +496,25 @@ class EquiUnetASSPEvo(_B21Net):
         ops.affine_pool(d1, ab_d1[0], ab_d1[1], p1, mode=2)
         self._fblock("encoder2", p1, None, t2, d2, stats, cs[1], ab_t2, ab_d2)
         ops.affine_pool(d2, ab_d2[0], ab_d2[1], p2, mode=2)
-        # levels 3-4: explicit normalisation (tap kernel; < 4 % of the elementwise traffic)
-        _, s = self._block("encoder3", p2, t3, d3, stats, cs[2])
-        ops.scale_pool(d3, s, full=d3, pooled=p3, mode=2)
+        # level 3 is folded as well when its planes are large enough for the sliding-window kernel (it removes five
+        # of the nine normalisation passes, two SE-gate launches and two scale passes per batch); level 4 (tap kernel,
+        # 16^3) keeps the explicit normalisation
+        h2 = f[2] // 2
+        fold3 = ops.fold_level3 and d // 4 >= 2 and h // 4 >= 8 and w // 4 >= 8 and \
+            all(ops.fold_supported(self._packed[k]) for k in self._FOLD3_CONVS)
+        if fold3:
+            ab_t3, ab_d3 = self._ab(ws, "ab_t3", n, f[2]), self._ab(ws, "ab_d3", n, f[2])
+            ab_u3 = self._ab(ws, "ab_u3", n, f[2])
+            fresh = "ab_c3" not in ws
+            ab_c3 = self._ab(ws, "ab_c3", n, f[2])
+            if fresh:  # the up-sampled half of the level-3 concat holds actual values: identity affine, set once
+                ab_c3[0][:, h2:] = 1.0
+                ab_c3[1][:, h2:] = 0.0
+            self._fblock("encoder3", p2, None, t3, d3, stats, cs[2], ab_t3, ab_d3)
+            ops.affine_pool(d3, ab_d3[0], ab_d3[1], p3, mode=2)
+        else:
+            _, s = self._block("encoder3", p2, t3, d3, stats, cs[2])
+            ops.scale_pool(d3, s, full=d3, pooled=p3, mode=2)
         _, s = self._block("encoder4", p3, t4, d4, stats, cs[3])
         ops.scale_pool(d4, s, full=d4, mode=0)
         pk = self._packed
@@ -516,14 +534,21 @@ class EquiUnetASSPEvo(_B21Net):
             cat1a, cat1b = cat1[..., :h0], cat1[..., h0:]
         self._fconvevo("bridge1", d1, ab_d1, cat1a, stats, (ab_c1[0][:, :h0], ab_c1[1][:, :h0]))
         self._fconvevo("bridge2", d2, ab_d2, cat2[..., :h1], stats, (ab_c2[0][:, :h1], ab_c2[1][:, :h1]))
-        self._convevo("bridge3", d3, cat3[..., :f[2] // 2], stats)
+        if fold3:
+            self._fconvevo("bridge3", d3, ab_d3, cat3[..., :h2], stats, (ab_c3[0][:, :h2], ab_c3[1][:, :h2]))
+        else:
+            self._convevo("bridge3", d3, cat3[..., :h2], stats)
 
         u = self._convevo("upconv3", assp, B("uc3", 8, f[3] // 4), stats)
-        ops.upsample2x(u, cat3[..., f[2] // 2:])
-        up3, s = self._block("decoder3", cat3, t3, B("up3", 4, f[2]), stats, cs[2])
-        ops.scale_pool(up3, s, full=up3, mode=0)
+        ops.upsample2x(u, cat3[..., h2:])
+        up3 = B("up3", 4, f[2])
+        if fold3:
+            self._fblock("decoder3", cat3, ab_c3, t3, up3, stats, cs[2], ab_t3, ab_u3)
+        else:
+            _, s = self._block("decoder3", cat3, t3, up3, stats, cs[2])
+            ops.scale_pool(up3, s, full=up3, mode=0)
         uc2 = B("uc2", 4, f[2] // 4)
-        self._fconvevo("upconv2", up3, None, uc2, stats, (ab_c2[0][:, h1:], ab_c2[1][:, h1:]))
+        self._fconvevo("upconv2", up3, ab_u3 if fold3 else None, uc2, stats, (ab_c2[0][:, h1:], ab_c2[1][:, h1:]))
         ops.upsample2x(uc2, cat2[..., h1:])  # interpolation weights sum to 1: the affine passes through unchanged
         up2 = B("up2", 2, f[1])
         self._fblock("decoder2", cat2, ab_c2, t2, up2, stats, cs[1], ab_t2, ab_u2)
@@ -535,7 +560,11 @@ class EquiUnetASSPEvo(_B21Net):
         out = ops.head_conv(up1, pk["out_conv.w"], pk["out_conv.bias"], scale=ab_u1[0], offset=ab_u1[1])
         deeps: List[torch.Tensor] = []
         if want_deep and self.deep_supervision:
-            deeps.append(ops.upsample_f32(ops.head_conv(up3, pk["deep3.0.w"], pk["deep3.0.bias"]), 4))
+            if fold3:
+                deeps.append(ops.upsample_f32(ops.head_conv(up3, pk["deep3.0.w"], pk["deep3.0.bias"], scale=ab_u3[0],
+                                                            offset=ab_u3[1]), 4))
+            else:
+                deeps.append(ops.upsample_f32(ops.head_conv(up3, pk["deep3.0.w"], pk["deep3.0.bias"]), 4))
             deeps.append(ops.upsample_f32(ops.head_conv(up2, pk["deep2.0.w"], pk["deep2.0.bias"], scale=ab_u2[0],
                                                         offset=ab_u2[1]), 2))
         return out, deeps

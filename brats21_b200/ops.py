@@ -213,6 +213,8 @@ use_march = True
 use_slide = True
 # folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations
 use_fold = True
+# folded EvoNorm on level 3 too (192-channel sliding-window convs with per-sample weights); tests flip it
+fold_level3 = True
 # level-1 concat of the folded path as two dense tensors (b21_conv3d_march_fwd_fold2); tests flip it
 split_concat = True
 # single-MUFU swish (tanh.approx) in the epilogue of the Cin = 8 input conv of the folded path; tests flip it

@@ -145,3 +145,27 @@ def test_v2_split_concat_matches_in_place_concat(width, shape, n):
         ops.split_concat = True
     rel = ((out_s - out_c).norm() / out_c.norm()).item()
     assert rel <= 1e-2, rel
+
+
+@pytest.mark.parametrize("width,shape,n", [(16, (16, 32, 48), 2), (48, (32, 64, 64), 1)])
+def test_v2_level3_fold_matches_explicit_level3(width, shape, n):
+    """Folding level 3 as well (64- / 192-channel sliding-window convs with per-sample weights, bridge3, the deep3
+    head) against the same network with level 3 on the explicit normalisation path and against the fp32 oracle."""
+    from brats21_b200 import ops
+    from oracle import nets, synth
+    net, params = _build(2, width, 93)
+    x = torch.cat([synth.volume(seed=s, shape=shape) for s in range(n)]).to(DEV)
+    with torch.no_grad():
+        ref, ref_deeps = nets.equiunet_v2_forward(params, x)
+    assert ops.fold_level3
+    out_f, deeps_f = net(x)
+    ops.fold_level3 = False
+    try:
+        out_e, deeps_e = net(x)
+    finally:
+        ops.fold_level3 = True
+    _check(out_f, ref)
+    for a, b in zip(deeps_f, ref_deeps):
+        _check(a, b)
+    assert ((out_f - out_e).norm() / out_e.norm()).item() <= 1.5e-2
+    assert ((deeps_f[0] - deeps_e[0]).norm() / deeps_e[0].norm()).item() <= 1.5e-2
