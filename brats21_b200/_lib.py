@@ -12,7 +12,7 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libb21.so"
+LIB_PATH = Path(os.environ["B21_LIB"]) if os.environ.get("B21_LIB") else _PKG / "libb21.so"  # B21_LIB: A/B runs of two builds
 STAT_SLOTS = 32
 
 _vp, _i, _f, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64

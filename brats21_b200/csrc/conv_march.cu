@@ -78,15 +78,23 @@ __device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int i
   return it;
 }
 
+// scout -> issuer message: everything the issuing thread needs for one input plane (48 bytes, three 16-byte words)
+struct PlaneMsg {
+  uint32_t a_lo, a_hi, b_lo, b_hi;   // A / B shared-memory descriptors of the plane's first tap / k-step
+  uint32_t col0, id0, id1, b1;       // accumulator column, instruction descriptors, B offset of the wrapped groups
+  uint32_t stage, accf_lo, accf_hi, pad;  // plane stage to release, ring slots to commit (0xffffffff = none / end)
+};
+constexpr int kMsgRing = 8;
+
 // KS = compile-time number of 16-channel k-steps (0: runtime loop).  With a runtime count the compiler emits a
 // branchy remainder loop around every tcgen05.mma (about 80 cycles of issue per MMA against 72 of execution at
 // N = 144, so the tensor pipe drains during the per-plane bookkeeping); fully unrolled, an MMA costs two uniform
 // 64-bit adds and the issue thread runs ahead of the pipe.
 template <int COUT, int NG, int KS>
-__global__ void __launch_bounds__(kMThreadsBase + NG * 128, 1)
+__global__ void __launch_bounds__(kMThreadsBase + NG * 128 + 32, 1)
 conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                   const ConvMarchParams p) {
-  constexpr int kMThreads = kMThreadsBase + NG * 128;
+  constexpr int kMThreads = kMThreadsBase + NG * 128 + 32;  // + the scout warp
   constexpr int PC = NG > 2 ? 16 : COUT;  // columns per epilogue pass
   constexpr uint32_t RING = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;  // accumulator slots in TMEM
   extern __shared__ uint8_t smem_raw[];
@@ -98,6 +106,8 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[NG][2][16];  // [epilogue group][double buffer][8 groups x (sum, sumsq)]
   __shared__ float s_bias[COUT];
+  __shared__ __align__(16) PlaneMsg msg_ring[kMsgRing];
+  __shared__ uint32_t msg_ready;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -121,6 +131,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmX2);
   }
+  if (threadIdx.x == 0) msg_ready = 0;
   if (threadIdx.x < NG * 32) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
   for (int c = threadIdx.x; c < COUT; c += kMThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
   if (p.merged) {
@@ -193,179 +204,171 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+  } else if (warp == 1 || warp == 2 + 4 * NG) {
+    // ------------------------------------------------------------------ MMA issuer (warp 1) + its scout (last warp)
+    // tcgen05.mma issue is close to synchronous (the pipe accepts one or two MMAs ahead), so every cycle the issuing
+    // thread spends on anything else is a cycle the tensor pipe idles.  Measured per plane on the 48 -> 48 layer
+    // (profiles/r01i_march_variants.md): 27 MMAs 1780 cycles, ring/border arithmetic 270, the two mbarrier waits 600-900
+    // (even when both phases completed long ago), commits 300.  The arithmetic and the waits therefore live on a SCOUT
+    // thread (one elected lane of the last warp): it walks the same plane sequence, waits for the plane's data
+    // (full barrier), for freshly claimed accumulator slots (acce barriers) and for the weights, and publishes a
+    // ready-made descriptor through a small shared-memory ring; the issuer only polls a counter, reads 48 bytes and
+    // issues.  The scout can never be more than `stages` planes ahead (it waits on the same full barriers), so a ring of
+    // 8 entries needs no back-pressure.
     if (elect_one()) {
       constexpr uint32_t lboB = (3 * COUT / 8) * 128, sboB = 128;
       constexpr uint32_t lboA = kMChunkBytes, sboA = kMHW * 16;
-      const uint64_t dA = nosw_desc(0, lboA, sboA), dB = nosw_desc(0, lboB, sboB);
-      const uint32_t idesc1 = umma_idesc_bf16(128, COUT), idesc2 = umma_idesc_bf16(128, 2 * COUT),
-                     idesc3 = umma_idesc_bf16(128, 3 * COUT);
-      const uint64_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);
-      const uint64_t bd0 = dB + uint64_t(w_addr >> 4);
-      const int ksteps = p.kc >> 1;
-      const int nkh = (p.variant & 16) ? 1 : 3;
-      // The per-plane bookkeeping (ring / border arithmetic, slot claims, barrier waits: several hundred cycles of a
-      // single dependent instruction stream) used to sit between the last MMA of one plane and the first MMA of the
-      // next, and the tensor pipe — whose queue holds only a few MMAs — drained meanwhile (~760 idle cycles per plane,
-      // measured with the B21_MARCH_VARIANT switches).  It is now software-pipelined: the descriptor of the NEXT plane
-      // is computed and its barriers are awaited BETWEEN the kh groups of the current plane's MMAs.
-      struct PlaneDesc {
-        uint64_t a_row, bq;
-        uint32_t col0, id0, id1, b1;       // b1 = B-descriptor offset of the wrapped column groups (len1 > 0)
-        uint32_t sg_lo, r_lo, stage, phase;
-        int ngroups, len1, accf_lo, accf_hi;  // ring slots to commit after the MMAs (-1 = none)
-        bool need_w;
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0, r_lo = 0;
-      int w_n = -1;
-      uint32_t w_par = 0;
-      int item = blockIdx.x, pi = 0;
-      bool have_item = false, pending_w = false;
-      MarchItem it;
-      it.n = it.h0 = it.w0 = it.d0 = it.Lc = 0;
-
-      // descriptor of the next valid input plane (pure arithmetic, no waits); false when this CTA's work is done
-      auto advance = [&](PlaneDesc& pd) -> bool {
-        for (;;) {
-          if (!have_item) {
-            if (item >= p.items) return false;
-            it = decode_item(p, item);
-            pi = 0;
-            r_lo = r_base;
-            have_item = true;
-            if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
-              w_n = it.n;
-              pending_w = true;
+      constexpr uint32_t kEnd = 0xffffffffu;
+      if (warp != 1) {
+        // ---------------------------------------------------------------- scout
+        const uint64_t dA = nosw_desc(0, lboA, sboA), dB = nosw_desc(0, lboB, sboB);
+        const uint32_t idesc1 = umma_idesc_bf16(128, COUT), idesc2 = umma_idesc_bf16(128, 2 * COUT),
+                       idesc3 = umma_idesc_bf16(128, 3 * COUT);
+        const uint64_t bd0 = dB + uint64_t(w_addr >> 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t sg_base = 0, next_fresh = 0, r_base = 0, claim_par = 0;
+        int w_n = -1;
+        uint32_t w_par = 0, k = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+          const MarchItem it = decode_item(p, item);
+          if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
+            w_n = it.n;
+            mbar_wait(&w_bar, w_par);
+            w_par ^= 1u;
+          }
+          uint32_t r_lo = r_base;
+          for (int i = 0; i <= it.Lc + 1; ++i) {
+            // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j; the lowest valid
+            // group of plane i sits in ring slot r_lo, which advances by one per plane once i >= 3.
+            if (i >= 3) r_lo = r_lo + 1 == RING ? 0 : r_lo + 1;
+            const int dz = it.d0 - 1 + i;
+            if (dz < 0 || dz >= p.D) continue;
+            const int jlo = i >= 2 ? 0 : 2 - i;
+            const int jhi = i + 1 <= it.Lc ? 2 : it.Lc + 1 - i;
+            const int ngroups = jhi - jlo + 1;
+            const uint32_t sg_lo = sg_base + uint32_t(i + jlo - 2);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              const uint32_t sg = sg_lo + uint32_t(g);
+              if (g < ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
+                uint32_t r = r_lo + uint32_t(g);
+                r = r >= RING ? r - RING : r;
+                mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
+                claim_par ^= 1u << r;
+                next_fresh = sg + 1;
+              }
+            }
+            mbar_wait_a(full0 + 8u * stage, phase);
+            const int room = int(RING - r_lo);
+            const int len0 = ngroups < room ? ngroups : room, len1 = ngroups - len0;  // at most one ring wrap
+            PlaneMsg m;
+            const uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
+            const uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
+            m.a_lo = uint32_t(a_row); m.a_hi = uint32_t(a_row >> 32);
+            m.b_lo = uint32_t(bq); m.b_hi = uint32_t(bq >> 32);
+            m.col0 = tmem_base + r_lo * COUT;
+            m.id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
+            m.id1 = len1 == 2 ? idesc2 : idesc1;
+            m.b1 = len1 ? uint32_t(len0) * COUT : 0u;  // 0: no ring wrap (a single MMA per tap and k-step)
+            m.stage = uint32_t(stage);
+            m.accf_lo = i >= 2 ? r_lo : kEnd;  // output plane so = i - 1 is complete after this plane
+            m.accf_hi = kEnd;
+            if (i == it.Lc && it.d0 + it.Lc >= p.D) {  // no plane i + 1 exists: so = i is complete as well
+              const uint32_t r = r_lo + uint32_t(1 - jlo);
+              m.accf_hi = r >= RING ? r - RING : r;
+            }
+            m.pad = 0;
+            uint4* dst = reinterpret_cast<uint4*>(&msg_ring[k & (kMsgRing - 1)]);
+            const uint4* src = reinterpret_cast<const uint4*>(&m);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+            ++k;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&msg_ready) = k;
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          if (pi > it.Lc + 1) {
-            sg_base += uint32_t(it.Lc);
-            r_base = (r_base + uint32_t(it.Lc)) % RING;
-            item += gridDim.x;
-            have_item = false;
-            continue;
-          }
-          const int i = pi++;
-          // column group j (0..2) = tap kd = 2 - j = output plane (local, 1-based) so = i - 1 + j; the lowest valid
-          // group of plane i sits in ring slot r_lo, which advances by one per plane once i >= 3.
-          if (i >= 3) r_lo = r_lo + 1 == RING ? 0 : r_lo + 1;
-          const int dz = it.d0 - 1 + i;
-          if (dz < 0 || dz >= p.D) continue;
-          const int jlo = i >= 2 ? 0 : 2 - i;
-          const int jhi = i + 1 <= it.Lc ? 2 : it.Lc + 1 - i;
-          pd.ngroups = jhi - jlo + 1;
-          pd.sg_lo = sg_base + uint32_t(i + jlo - 2);
-          pd.r_lo = r_lo;
-          const int room = int(RING - r_lo);
-          const int len0 = pd.ngroups < room ? pd.ngroups : room;  // at most one ring wrap
-          pd.len1 = pd.ngroups - len0;
-          pd.col0 = tmem_base + ((p.variant & 2048) ? 0u : r_lo * COUT);  // debug bit11: constant accumulator address
-          pd.id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
-          pd.id1 = pd.len1 == 2 ? idesc2 : idesc1;
-          pd.b1 = uint32_t(len0) * COUT;
-          pd.a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
-          pd.bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
-          pd.stage = uint32_t(stage);
-          pd.phase = phase;
-          pd.accf_lo = i >= 2 ? int(r_lo) : -1;  // output plane so = i - 1 is complete after this plane
-          pd.accf_hi = -1;
-          if (i == it.Lc && it.d0 + it.Lc >= p.D) {  // no plane i + 1 exists: so = i is complete as well
-            uint32_t r = r_lo + uint32_t(1 - jlo);
-            pd.accf_hi = int(r >= RING ? r - RING : r);
-          }
-          pd.need_w = pending_w;
-          pending_w = false;
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-          return true;
+          sg_base += uint32_t(it.Lc);
+          r_base = (r_base + uint32_t(it.Lc)) % RING;
         }
-      };
-      // everything the plane's first MMA has to wait for
-      auto acquire = [&](const PlaneDesc& pd) {
-        if (pd.need_w) {
-          mbar_wait(&w_bar, w_par);
-          w_par ^= 1u;
+        msg_ring[k & (kMsgRing - 1)].stage = kEnd;  // end marker
+        ++k;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&msg_ready) = k;
+      } else {
+        // ---------------------------------------------------------------- issuer
+        const uint64_t a_step = 2u * (lboA >> 4), b_step = 2u * (lboB >> 4);
+        const int ksteps = p.kc >> 1;
+        const int nkh = (p.variant & 4096) ? 0 : ((p.variant & 16) ? 1 : 3);  // debug: bit4 one row of taps, bit12 no MMAs
+        for (uint32_t k = 0;; ++k) {
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile uint32_t*>(&msg_ready) <= k) {
+            if (++spins > (1u << 28)) {
+              printf("b21: march issuer starved block %d plane %u\n", blockIdx.x, k);
+              __trap();
+            }
+          }
+          __threadfence_block();
+          PlaneMsg m;
+          {
+            const uint4* src = reinterpret_cast<const uint4*>(&msg_ring[k & (kMsgRing - 1)]);
+            uint4* dst = reinterpret_cast<uint4*>(&m);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+          }
+          if (m.stage == kEnd) break;
           tc_fence_after();
-        }
+          const uint64_t a_row = (uint64_t(m.a_hi) << 32) | m.a_lo, bq0 = (uint64_t(m.b_hi) << 32) | m.b_lo;
+          if constexpr (KS > 0) {
+            constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
+            if (m.b1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          const uint32_t sg = pd.sg_lo + uint32_t(g);
-          if (g < pd.ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
-            uint32_t r = pd.r_lo + uint32_t(g);
-            r = r >= RING ? r - RING : r;
-            mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
-            claim_par ^= 1u << r;
-            next_fresh = sg + 1;
-          }
-        }
-        mbar_wait_a(full0 + 8u * pd.stage, pd.phase);
-        tc_fence_after();
-      };
-      // the MMAs of one kh row of taps
-      auto issue = [&](const PlaneDesc& pd, int kh) {
-        if (kh >= nkh) return;
-        if constexpr (KS > 0) {
-          constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
-          const uint64_t a0 = pd.a_row + uint64_t(kh * kMHW), b0 = pd.bq + uint64_t(kh * 3 * KS) * kBStep;
-          if (pd.len1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
+              for (int kh = 0; kh < 3; ++kh) {
+                if (kh < nkh) {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+                  for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-              for (int ks = 0; ks < KS; ++ks)
-                umma_bf16(pd.col0, a0 + uint64_t(kw) + uint64_t(ks) * kAStep, b0 + uint64_t(kw * KS + ks) * kBStep, pd.id0, 1u);
+                    for (int ks = 0; ks < KS; ++ks)
+                      umma_bf16(m.col0, a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep,
+                                bq0 + uint64_t((kh * 3 + kw) * KS + ks) * kBStep, m.id0, 1u);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                if (kh < nkh) {
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                      const uint64_t ad = a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep;
+                      const uint64_t bd = bq0 + uint64_t((kh * 3 + kw) * KS + ks) * kBStep;
+                      umma_bf16(m.col0, ad, bd, m.id0, 1u);
+                      umma_bf16(tmem_base, ad, bd + m.b1, m.id1, 1u);
+                    }
+                  }
+                }
+              }
             }
           } else {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-              for (int ks = 0; ks < KS; ++ks) {
-                const uint64_t ad = a0 + uint64_t(kw) + uint64_t(ks) * kAStep;
-                const uint64_t bd = b0 + uint64_t(kw * KS + ks) * kBStep;
-                umma_bf16(pd.col0, ad, bd, pd.id0, 1u);
-                umma_bf16(tmem_base, ad, bd + pd.b1, pd.id1, 1u);
+            uint64_t a_kh = a_row, bq = bq0;
+            for (int kh = 0; kh < nkh; ++kh, a_kh += kMHW) {
+              uint64_t a_tap = a_kh;
+              for (int kw = 0; kw < 3; ++kw, ++a_tap) {
+                uint64_t ad = a_tap;
+                for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
+                  umma_bf16(m.col0, ad, bq, m.id0, 1u);
+                  if (m.b1 != 0) umma_bf16(tmem_base, ad, bq + m.b1, m.id1, 1u);
+                }
               }
             }
           }
-        } else {
-          uint64_t a_tap = pd.a_row + uint64_t(kh * kMHW);
-          uint64_t bq = pd.bq + uint64_t(kh * 3 * ksteps) * b_step;
-          for (int kw = 0; kw < 3; ++kw, ++a_tap) {
-            uint64_t ad = a_tap;
-            for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
-              umma_bf16(pd.col0, ad, bq, pd.id0, 1u);
-              if (pd.len1 != 0) umma_bf16(tmem_base, ad, bq + pd.b1, pd.id1, 1u);
-            }
-          }
+          umma_commit_a(empty0 + 8u * m.stage);
+          if (m.accf_lo != kEnd) umma_commit_a(accf0 + 8u * m.accf_lo);
+          if (m.accf_hi != kEnd) umma_commit_a(accf0 + 8u * m.accf_hi);
         }
-      };
-      auto finish = [&](const PlaneDesc& pd) {
-        if (p.variant & 512) mbar_arrive_a(empty0 + 8u * pd.stage);  // debug (only with bit2): one commit less per plane
-        else umma_commit_a(empty0 + 8u * pd.stage);
-        if (pd.accf_lo >= 0) umma_commit_a(accf0 + 8u * uint32_t(pd.accf_lo));
-        if (pd.accf_hi >= 0) umma_commit_a(accf0 + 8u * uint32_t(pd.accf_hi));
-      };
-
-      PlaneDesc cur, nxt;
-      bool has = advance(cur);
-      if (has) acquire(cur);
-      while (has) {
-        issue(cur, 0);
-        const bool has_next = advance(nxt);
-        issue(cur, 1);
-        // new weights are loaded only after every MMA on the old ones has completed: that wait cannot be taken early
-        // (with a single k-step per tap the plane's MMAs are too short to cover the wait for the next plane's TMA)
-        const bool early = has_next && !nxt.need_w && KS != 1 && !(p.variant & 1024);
-        if (early) acquire(nxt);
-        issue(cur, 2);
-        finish(cur);
-        if (has_next && !early) acquire(nxt);
-        cur = nxt;
-        has = has_next;
       }
     }
   } else {
@@ -627,7 +630,7 @@ static int launch_march_ng(const CUtensorMap& tm, const CUtensorMap& tm2, const 
                                   kMSmemBudget));
     attr_set = true;
   }
-  conv_march_kernel<COUT, NG, KS><<<grid, kMThreadsBase + NG * 128, smem_bytes, stream>>>(tm, tm2, p);
+  conv_march_kernel<COUT, NG, KS><<<grid, kMThreadsBase + NG * 128 + 32, smem_bytes, stream>>>(tm, tm2, p);
   B21_LAUNCH_CHECK("conv_march_kernel");
   return B21_OK;
 }
