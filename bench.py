@@ -132,6 +132,29 @@ def cpu_window_forward_seconds(version: int, repeats: int = 1, shape=ROI):
     return times
 
 
+def torch_gpu_window_seconds(version: int, dev, batch: int = 4):
+    """Context for the headline: the reference's network code (oracle port, torch/cuDNN) on the SAME GPU
+    under torch.autocast(bf16) — its default mixed-precision mode — for one batch of 128^3 windows.  Baseline only."""
+    from oracle import nets, synth  # CHECKER/BASELINE use of oracle/ (part of the cpu_baseline leg)
+    params = {k: v.to(dev) for k, v in synth.make_params(version, WIDTH, 93 if version == 2 else 123).items()}
+    fwd = nets.equiunet_v2_forward if version == 2 else nets.equiunet_v1_forward
+    x = torch.cat([synth.volume(seed=s, shape=ROI) for s in range(batch)]).to(dev)
+    best = None
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fwd(params, x, deep_supervision=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+    del params, x
+    torch.cuda.empty_cache()
+    return best * 1e-3 / batch
+
+
 def windows_per_volume(wl):
     return 18 * (8 if wl["tta"] == "flip8" else 1) * len(wl.get("ensemble", (0,)))
 
@@ -383,6 +406,14 @@ def run_b200(args, wl, rank, local_rank, world):
             line["cpu_baseline"] = {"value": 1.0 / (nwin * t), "unit": "volumes/s", "cores": os.cpu_count(),
                                     "kind": "port", "sample": f"1 of {nwin} windows (V{wl['version']} forward 128^3 "
                                     f"fp32, {t:.1f} s), extrapolated to the volume"}
+            try:
+                tw = torch_gpu_window_seconds(wl["version"], dev)
+                line["torch_gpu_baseline"] = {
+                    "value": 1.0 / (nwin * tw), "unit": "volumes/s", "kind": "port",
+                    "sample": f"reference network code (torch/cuDNN, autocast bf16) on this GPU: best of 3 batches of 4 "
+                              f"windows, {tw * 1e3:.1f} ms per window, network forward only, extrapolated to {nwin} windows"}
+            except Exception as exc:  # noqa: BLE001  (a baseline must never break the bench line)
+                line["torch_gpu_baseline"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
