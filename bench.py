@@ -27,7 +27,12 @@ import sys
 import threading
 import time
 
-import torch
+# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout when the launcher's
+# environment has NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
