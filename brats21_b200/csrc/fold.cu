@@ -32,7 +32,7 @@ __device__ __forceinline__ uint4 f_pack8(const float* f) {
 // ------------------------------------------------------------------------------------------ statistics -> (A, B)
 // One block per sample.  A[n][c] = a_c * s_c, B[n][c] = beta_c * s_c with s_c = 1 when there is no SE gate, else the
 // MONAI ResidualSELayer gate 1 + sigmoid(W2 relu(W1 m + b1) + b2) on m_c = a_c * mean(S_c) + beta_c.
-__global__ void evo_se_affine_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(1024) evo_se_affine_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, const float* __restrict__ chan_sum,
                                      const float* __restrict__ w1, const float* __restrict__ b1,
                                      const float* __restrict__ w2, const float* __restrict__ b2,
@@ -212,7 +212,9 @@ extern "C" int b21_evo_se_affine(const double* stats, const float* gamma, const 
     B21_CUDA(cudaFuncSetAttribute(evo_se_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  evo_se_affine_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(
+  // the SE variant stages up to 147 KB of MLP weights and runs two dependent mat-vecs in ONE block per sample: it is
+  // latency-bound, so it gets 32 warps
+  evo_se_affine_kernel<<<n, chan_sum ? 1024 : 256, smem, (cudaStream_t)stream>>>(
       stats, gamma, beta, chan_sum, w1, b1, w2, b2, a_out, b_out, ldab, n, c, hidden, nvox, eps);
   B21_LAUNCH_CHECK("evo_se_affine_kernel");
   return B21_OK;
