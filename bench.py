@@ -27,10 +27,11 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout when the launcher's
-# environment has NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: NCCL writes its "NCCL version ..." banner (any NCCL_DEBUG level >= VERSION) and
+# its debug log to stdout unless told otherwise, so send them to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # that level exists only to print the banner
+    os.environ.pop("NCCL_DEBUG")
 
 import torch  # noqa: E402
 
