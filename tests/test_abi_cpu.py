@@ -93,3 +93,41 @@ def test_state_dict_contract_and_factories():
         v1(torch.zeros(1, 4, 8, 8, 8))
     with pytest.raises(RuntimeError):
         inferers.sliding_window_inference(torch.zeros(1, 4, 8, 8, 8), 8, 1, v1)
+
+
+def test_header_arity_matches_ctypes_signatures():
+    """Every prototype of include/b21.h has as many parameters as its ctypes binding (brats21_b200/_lib.py)."""
+    header = open(os.path.join(ROOT, "include", "b21.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|long long|const char\*)\s+(b21_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(protos) >= 50
+    seen = set()
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        seen.add(name)
+        if name in ("b21_last_error", "b21_version"):
+            assert n == 0
+            continue
+        assert name in _lib._SIGNATURES, name
+        assert n == len(_lib._SIGNATURES[name]), f"{name}: header has {n} parameters, ctypes binding {len(_lib._SIGNATURES[name])}"
+    assert seen == set(_lib.exported_symbols())
+
+
+def test_pre_post_entry_points_validate_arguments_before_any_cuda_call():
+    lib = _lib.load()
+    err = lambda: lib.b21_last_error().decode()  # noqa: E731
+    assert lib.b21_keep_components(None, None, 8, 8, 8, 10, None) == -1 and "null" in err()
+    assert lib.b21_keep_components(1, 1, 0, 8, 8, 10, None) == -1 and "dims" in err()
+    assert lib.b21_replace_rare_labels(1, 1, 8, 8, 8, 20, 5, None) == -1 and "axis" in err()
+    assert lib.b21_replace_rare_labels(1, 1, 8, 8, 8, -1, 2, None) == -1 and "thresh" in err()
+    assert lib.b21_labels_to_channels(None, None, 8, None) == -1
+    assert lib.b21_foreground_bbox(None, 4, 8, 8, 8, None, None) == -1 and "null" in err()
+    assert lib.b21_nonzero_stats(1, 0, 8, 8, 8, 1, 1, None) == -1 and "dims" in err()
+    assert lib.b21_normalize_crop_pad(1, 1, 17, 8, 8, 8, 1, 1, 8, 8, 8, 0, 0, 0, 0.0, None) == -1
+    assert lib.b21_grad_centralize(None, 0, None) == -1
+    assert lib.b21_keep_components_workspace_bytes(1000) == 8016
+    assert lib.b21_replace_rare_workspace_bytes(20) == 4 * (258 + 2 * 256 * 20)
+    # split-input conv: the second tensor is mandatory and the channel split must be chunk-aligned
+    assert lib.b21_conv3d_march_fwd_fold2(1, 24, 24, None, 24, 1, 0, None, None, 1, 48, None, None, 1, 1, 8, 16, 16, 48, 48,
+                                          None) == -1 and "second input" in err()
