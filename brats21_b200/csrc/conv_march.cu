@@ -54,7 +54,9 @@ struct ConvMarchParams {
   FoldExtras ex;
   int split;    // 8-channel chunks [split, kc) come from a SECOND tensor (tmX2): channel concat without a concat buffer
   int merged;   // Cin == 8 dense input (ld = 8): (w, c) merged into one tensor-map dimension, chunk 1 is zero in smem
-  int variant;  // debug (B21_MARCH_VARIANT): bit2 no TMA loads, bit3 no stores, bit4 three taps only, bit5 no epilogue math/stores, bit6 no TMEM ld/st
+  int variant;  // debug (B21_MARCH_VARIANT, see profiles/r01i_march_variants.md): 4 no TMA loads, 8 no stores, 16 one kh row of
+                // taps only, 32 epilogue handshake only, 64 no TMEM ld/st, 128 two epilogue groups for the input conv,
+                // 256 runtime k-step loop, 4096 no MMAs
 };
 
 __device__ __forceinline__ uint64_t nosw_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
