@@ -67,3 +67,21 @@ def test_preprocess_crop_bbox_and_zero_background():
     for c in range(img.shape[0]):
         v = core[c][crop[c] != 0]
         assert abs(v.mean()) < 1e-4 and abs(v.std() - 1) < 1e-4
+
+
+def test_pad_back_inverts_crop_and_pad():
+    """postprocess.pad_back (pure slicing, device-agnostic) undoes oracle.preprocess's crop + pad bookkeeping."""
+    import torch
+    from brats21_b200.postprocess import pad_back
+    from brats21_b200.preprocess import CropMeta
+    img = pp.synth_raw(2, (2, 21, 18, 27))
+    out, start, end, pb, pa = pp.preprocess(img, 8)
+    meta = CropMeta(tuple(img.shape[1:]), tuple(start), tuple(end), tuple(int(v) for v in pb), tuple(int(v) for v in pa))
+    marker = torch.arange(out[0].size, dtype=torch.float32).reshape(out.shape[1:]) + 1.0
+    back = pad_back(marker, meta)
+    assert tuple(back.shape) == img.shape[1:]
+    core = marker[pb[0]:marker.shape[0] - pa[0], pb[1]:marker.shape[1] - pa[1], pb[2]:marker.shape[2] - pa[2]]
+    assert torch.equal(back[start[0]:end[0], start[1]:end[1], start[2]:end[2]], core)
+    outside = back.clone()
+    outside[start[0]:end[0], start[1]:end[1], start[2]:end[2]] = 0
+    assert outside.abs().max().item() == 0
