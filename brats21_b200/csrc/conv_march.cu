@@ -16,8 +16,19 @@
 //     D[128, 3*Cout] += A[128, Cin] * [W(kd=2) | W(kd=1) | W(kd=0)], whose three column groups belong to output
 //     planes d'-1, d', d'+1.  TMEM holds a ring of per-output-plane accumulators (Cout fp32 columns each); the three
 //     groups are adjacent ring slots.  N = 144 instead of 48 amortises the A-tile read over 3x the math.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (tcgen05.ld ->
-//     + bias -> GroupNorm/EvoNorm group statistics -> bf16 NDHWC store) overlapped with the MMAs of later planes.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2 .. 2+4*NG-1 = NG epilogue groups of
+//     four warps (tcgen05.ld -> + bias / bias table -> GroupNorm/EvoNorm group statistics -> [swish] -> bf16 NDHWC
+//     store [-> SE channel sums]) that take the output planes round-robin and overlap with the MMAs of later planes,
+//     last warp = SCOUT.  tcgen05.mma issue is nearly synchronous (the pipe accepts one or two MMAs ahead), so the
+//     issuing thread does nothing but issue and commit: the scout walks the same plane sequence, does the ring / border
+//     arithmetic, waits on the mbarriers (plane data, freshly claimed accumulator slots, weights) and hands a 48-byte
+//     ready-made descriptor per plane to the issuer through a shared-memory ring.
+//   * Template parameters: COUT; NG = epilogue groups (2; 4 with 16-column passes for the Cin = 8 input conv, whose 9 MMAs
+//     per plane leave the epilogue on the critical path); KS = compile-time k-steps per tap (two uniform adds per MMA
+//     instead of a branchy remainder loop; 0 = runtime loop).
+//   * Input variants: `merged` (Cin = 8, dense): the plane is ONE TMA box of 18 rows x 160 B over a merged (w, c)
+//     dimension instead of 180 rows x 16 B, and the zero second k-chunk is written once; `split` (b21_..._fold2): the
+//     8-channel chunks come from TWO tensors, i.e. a channel concat is read in place from its two dense producers.
 //
 // Replaces torch.nn.Conv3d(k=3, padding=1) at networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201
 // for the layers whose weights fit in shared memory (54 * ceil16(Cin) * Cout bytes); other shapes use conv_tap.cu.
