@@ -7,7 +7,7 @@
 //     at most `thresh` voxels are replaced, slice by slice along one axis, by the value of the nearest voxel of the
 //     same slice that carries a kept label (scipy griddata(method="nearest"));
 //   * ConvertToMultiChannelBasedOnBratsClasses (MONAI): label map -> (TC, WT, ET) channels.
-// All integer work: bit-exact against the oracle (oracle/postproc.py).  HBM traffic is a few passes over a 9 MB
+// All integer work: bit-exact against the oracle (oracle/prepost.py).  HBM traffic is a few passes over a 9 MB
 // label volume + a 36 MB int32 parent array, i.e. launch-latency bound; the kernels are plain coalesced grid-stride
 // loops sized in multiples of the SM count.
 #include "host_common.h"

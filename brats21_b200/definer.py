@@ -86,4 +86,6 @@ def make_optimizer(args: argparse.Namespace, model: torch.nn.Module):
     trainable = [p for p in model.parameters() if p.requires_grad]
     return Ranger2020(trainable, lr=args.learning_rate, alpha=0.5, k=6, N_sma_threshhold=5, betas=(.95, 0.999),
                       eps=1e-5, weight_decay=args.weight_decay, use_gc=getattr(args, "use_gc", False),
-                      gc_conv_only=getattr(args, "gc_conv_only", False))
+                      use_gcnorm=getattr(args, "use_gcnorm", False), normloss=getattr(args, "normloss", False),
+                      normloss_factor=getattr(args, "normloss_factor", 1e-4),
+                      gc_conv_only=getattr(args, "gc_conv_only", False), gc_loc=True)

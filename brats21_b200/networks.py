@@ -104,6 +104,7 @@ class _B21Net(nn.Module):
 
     def _init_runtime(self):
         self._packed: Dict[str, object] = {}
+        self._aliases: List[Tuple[torch.Tensor, torch.Tensor]] = []  # (fp32 view or copy, source parameter)
         self._pack_key = None
         self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self.skip_deep_heads_in_eval = False  # set by the inference wrappers (they discard the deep heads)
@@ -131,20 +132,40 @@ class _B21Net(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _ensure_packed(self):
+        """Packed bf16 conv weights follow the parameters: rebuilt when a parameter's storage changed, re-packed IN
+        PLACE (same buffers, so captured CUDA graphs stay valid) when only its version counter moved — an optimizer
+        step (Ranger2020.step bumps the counters after its fused raw-pointer update), ``load_state_dict`` / ``copy_``."""
         key = self._param_key()
-        if key != self._pack_key:
-            self._packed = {}
+        if key == self._pack_key:
+            return
+        if self._pack_key is not None and len(key) == len(self._pack_key) and \
+                all(a[0] == b[0] for a, b in zip(key, self._pack_key)):
+            self._refresh_packed()
+        else:
+            self._packed, self._aliases, self._graphs = {}, [], {}
             self._pack()
-            self._pack_key = key
+        self._pack_key = key
+
+    def _refresh_packed(self):
+        for v in self._packed.values():
+            if isinstance(v, ops.PackedConv):
+                v.refresh()
+        for dst, src in self._aliases:
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src.detach().reshape(dst.shape))
 
     def _pc(self, name: str, conv: nn.Conv3d, cin_padded: Optional[int] = None):
         self._packed[name] = ops.PackedConv(conv.weight, conv.bias, cin_padded=cin_padded)
 
     def _vec(self, name: str, t: torch.Tensor):
-        self._packed[name] = t.detach().reshape(-1).to(torch.float32).contiguous()
+        v = t.detach().reshape(-1).to(torch.float32).contiguous()
+        self._packed[name] = v
+        self._aliases.append((v, t))
 
     def _mat(self, name: str, t: torch.Tensor):
-        self._packed[name] = t.detach().to(torch.float32).reshape(t.shape[0], -1).contiguous()
+        v = t.detach().to(torch.float32).reshape(t.shape[0], -1).contiguous()
+        self._packed[name] = v
+        self._aliases.append((v, t))
 
     # ---- workspaces
     def _buf(self, ws, name, shape, dtype=torch.bfloat16):
@@ -190,8 +211,6 @@ class _B21Net(nn.Module):
             return self.forward_packed(x8, want_deep=False)[0]
         key = (x8.data_ptr(), tuple(x8.shape), tuple(x8.stride()), ops.use_fold, ops.use_march, ops.use_slide,
                ops.use_point)
-        if self._graphs.get("pack_key") != self._pack_key:  # weights changed: every captured graph is stale
-            self._graphs = {"pack_key": self._pack_key}
         entry = self._graphs.get(key)
         if entry is None:
             self.forward_packed(x8, want_deep=False)  # warm-up: workspaces, lazily packed/folded weights, attributes

@@ -19,8 +19,37 @@ def _ld(t: torch.Tensor) -> int:
     return ld
 
 
+# When set to a list, every HBM-bound launch appends (start_event, end_event, algorithmic_bytes, kind): bench.py's
+# `hbm` roofline block (SURVEY.md §8d byte counts: bf16 activations read once / written once, fp32 accumulators RMW).
+hbm_profile = None
+
+
+class _hbm:
+    __slots__ = ("kind", "nbytes", "e0")
+
+    def __init__(self, kind: str, nbytes: float):
+        self.kind, self.nbytes, self.e0 = kind, nbytes, None
+
+    def __enter__(self):
+        if hbm_profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and hbm_profile is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            hbm_profile.append((self.e0, e1, float(self.nbytes), self.kind))
+        return False
+
+
 class PackedConv:
-    """bf16 weight repacked for the implicit-GEMM kernels: [k^3][cout_padded][cin_padded] (+ fp32 bias)."""
+    """bf16 weight repacked for the implicit-GEMM kernels: [k^3][cout_padded][cin_padded] (+ fp32 bias).
+
+    ``w32`` / ``bias`` alias the live fp32 parameter storage whenever the parameter is already fp32 and contiguous, so
+    after an in-place parameter update (optimizer step) ``refresh()`` re-runs the packing kernels INTO THE SAME
+    BUFFERS: pointers captured by CUDA graphs, tensor maps and the per-sample fold buffers stay valid."""
 
     def __init__(self, weight: torch.Tensor, bias, cin_padded: int | None = None, transpose_flip: bool = False):
         assert weight.is_cuda and weight.dim() == 5
@@ -32,10 +61,10 @@ class PackedConv:
         self.cout, self.cin, self.cin_true = rows, cin_padded, inner
         self.cout_padded = _lib.load().b21_conv_cout_padded(rows)
         self.w = torch.empty((self.taps, self.cout_padded, cin_padded), dtype=torch.bfloat16, device=weight.device)
-        w32 = weight.detach().to(torch.float32).contiguous()
-        self.w32, self.cin_padded, self._fold = w32, cin_padded, {}
-        call("b21_pack_conv_weight", ptr(w32), ptr(self.w), cout, cin, cin_padded, k, int(transpose_flip),
-             stream_ptr())
+        self._src_w, self._src_b, self._tf = weight, bias, bool(transpose_flip)
+        self._wshape = (cout, cin)
+        self.w32 = weight.detach().to(torch.float32).contiguous()
+        self.cin_padded, self._fold = cin_padded, {}
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
         lib = _lib.load()
         self.point_ok = k == 1 and bool(lib.b21_conv_point_supported(cin_padded, rows))
@@ -44,15 +73,32 @@ class PackedConv:
         if k == 3 and lib.b21_conv_march_supported(cin_padded, rows):
             nbytes = lib.b21_conv_march_weight_bytes(cin_padded, rows)
             self.w_march = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
-            call("b21_pack_conv_weight_march", ptr(w32), ptr(self.w_march), cout, cin, int(transpose_flip),
-                 stream_ptr())
         # sliding-window packing (k = 3, 16 <= cin <= 96, weights streamed per tap)
         self.w_slide = None
         if k == 3 and self.w_march is None and lib.b21_conv_slide_supported(cin_padded, rows):
             nbytes = lib.b21_conv_slide_weight_bytes(cin_padded, rows)
             self.w_slide = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
-            call("b21_pack_conv_weight_slide", ptr(w32), ptr(self.w_slide), cout, cin, int(transpose_flip),
+        self._launch_packs()
+
+    def _launch_packs(self):
+        cout, cin = self._wshape
+        tf = int(self._tf)
+        call("b21_pack_conv_weight", ptr(self.w32), ptr(self.w), cout, cin, self.cin_padded, self.k, tf, stream_ptr())
+        if self.w_march is not None:
+            call("b21_pack_conv_weight_march", ptr(self.w32), ptr(self.w_march), cout, cin, tf, stream_ptr())
+        if self.w_slide is not None:
+            call("b21_pack_conv_weight_slide", ptr(self.w32), ptr(self.w_slide), cout, cin, tf, stream_ptr())
+        if "ws" in self._fold:
+            call("b21_border_weight_sums", ptr(self.w32), ptr(self._fold["ws"]), self.cout, self.cin_true, self.taps,
                  stream_ptr())
+
+    def refresh(self):
+        """Re-pack after the source parameters changed in place (same storage): buffers are re-used."""
+        if self.w32.data_ptr() != self._src_w.data_ptr():  # the fp32 view was a converted copy: bring it up to date
+            self.w32.copy_(self._src_w.detach())
+        if self.bias is not None and self.bias.data_ptr() != self._src_b.data_ptr():
+            self.bias.copy_(self._src_b.detach())
+        self._launch_packs()
 
 
 def new_stats(n: int, device) -> torch.Tensor:
@@ -93,6 +139,8 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
     if prof is not None:
         e1.record()
         prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (kind, cin, pw.cout, pw.taps, d)))
+        if kind == "point" and hbm_profile is not None:
+            hbm_profile.append((e0, e1, 2.0 * n * d * h * w * (cin + pw.cout), "conv1x1"))
     return out
 
 
@@ -192,6 +240,8 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
         e1.record()
         kind = "point" if pw.taps == 1 else ("march" if pw.w_march is not None else "slide")
         prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (kind, cin, pw.cout, pw.taps, d)))
+        if kind == "point" and hbm_profile is not None:
+            hbm_profile.append((e0, e1, 2.0 * n * d * h * w * (cin + pw.cout), "conv1x1"))
     return out
 
 
@@ -199,8 +249,9 @@ def affine_pool(x, a_in, b_in, pooled, mode=2):
     """pooled = MaxAvgPool (mode 2) / MaxPool (mode 1) of (A[n][c] * x + B[n][c])."""
     n, d, h, w, c = x.shape
     assert a_in.shape == (n, c) and a_in.stride(0) == b_in.stride(0)
-    call("b21_affine_pool", ptr(x), _ld(x), ptr(a_in), ptr(b_in), a_in.stride(0), ptr(pooled), _ld(pooled), mode,
-         n, d, h, w, c, stream_ptr())
+    with _hbm("affine_pool", 2.0 * n * d * h * w * c * (1 + (2 if mode == 2 else 1) / 8)):
+        call("b21_affine_pool", ptr(x), _ld(x), ptr(a_in), ptr(b_in), a_in.stride(0), ptr(pooled), _ld(pooled), mode,
+             n, d, h, w, c, stream_ptr())
     return pooled
 
 
@@ -236,8 +287,9 @@ def norm_apply(x, stats, gamma, beta, mode, out=None, chan_sum=None, eps=1e-5):
     n, d, h, w, c = x.shape
     if out is None:
         out = x
-    call("b21_norm_apply", ptr(x), _ld(x), ptr(out), _ld(out), ptr(stats), ptr(gamma), ptr(beta), ptr(chan_sum),
-         mode, n, d * h * w, c, eps, stream_ptr())
+    with _hbm("norm_apply", 4.0 * n * d * h * w * c):
+        call("b21_norm_apply", ptr(x), _ld(x), ptr(out), _ld(out), ptr(stats), ptr(gamma), ptr(beta), ptr(chan_sum),
+             mode, n, d * h * w, c, eps, stream_ptr())
     return out
 
 
@@ -252,14 +304,18 @@ def se_gate(chan_sum, w1, b1, w2, b2, nvox):
 def scale_pool(x, scale=None, full=None, pooled=None, mode=0):
     """mode 0: full = x*scale; 1: max-pool; 2: [max|avg]-pool (writes 2C channels)."""
     n, d, h, w, c = x.shape
-    call("b21_scale_pool", ptr(x), _ld(x), ptr(scale), ptr(full), _ld(full) if full is not None else 0,
-         ptr(pooled), _ld(pooled) if pooled is not None else 0, mode, n, d, h, w, c, stream_ptr())
+    nb = 2.0 * n * d * h * w * c * (1 + (1 if full is not None else 0) +
+                                    ((2 if mode == 2 else 1) / 8 if pooled is not None else 0))
+    with _hbm("scale_pool", nb):
+        call("b21_scale_pool", ptr(x), _ld(x), ptr(scale), ptr(full), _ld(full) if full is not None else 0,
+             ptr(pooled), _ld(pooled) if pooled is not None else 0, mode, n, d, h, w, c, stream_ptr())
 
 
 def upsample2x(x, out):
     n, d, h, w, c = x.shape
     assert out.shape == (n, 2 * d, 2 * h, 2 * w, c)
-    call("b21_upsample2x", ptr(x), _ld(x), ptr(out), _ld(out), n, d, h, w, c, stream_ptr())
+    with _hbm("upsample2x", 2.0 * n * d * h * w * c * 9):
+        call("b21_upsample2x", ptr(x), _ld(x), ptr(out), _ld(out), n, d, h, w, c, stream_ptr())
     return out
 
 
@@ -279,8 +335,9 @@ def head_conv(x, weight, bias, scale=None, out=None, offset=None):
         out = torch.empty((n, k, d, h, w), dtype=torch.float32, device=x.device)
     ldso = scale.stride(0) if scale is not None else (offset.stride(0) if offset is not None else c)
     assert offset is None or scale is None or offset.stride(0) == scale.stride(0)
-    call("b21_head_conv", ptr(x), _ld(x), ptr(scale), ptr(offset), ldso, ptr(weight), ptr(bias), ptr(out), n,
-         d * h * w, c, k, stream_ptr())
+    with _hbm("head_conv", n * d * h * w * (2.0 * c + 4.0 * k)):
+        call("b21_head_conv", ptr(x), _ld(x), ptr(scale), ptr(offset), ldso, ptr(weight), ptr(bias), ptr(out), n,
+             d * h * w, c, k, stream_ptr())
     return out
 
 
@@ -299,8 +356,9 @@ def pack_windows(vol, out, origins, perm=(0, 1, 2), flip=(0, 0, 0), vol_index=No
     b, d, h, w, cpad = out.shape
     assert vol.dtype == torch.float32 and vol.is_contiguous() and out.is_contiguous() and len(origins) == b
     flat = [c for o in origins for c in o]
-    call("b21_pack_windows", ptr(vol), vc, vd, vh, vw, ptr(out), cpad, b, d, h, w, _iarr(flat),
-         _iarr(vol_index) if vol_index is not None else None, _iarr(perm), _iarr(flip), stream_ptr())
+    with _hbm("pack_windows", b * d * h * w * (4.0 * vc + 2.0 * cpad)):
+        call("b21_pack_windows", ptr(vol), vc, vd, vh, vw, ptr(out), cpad, b, d, h, w, _iarr(flat),
+             _iarr(vol_index) if vol_index is not None else None, _iarr(perm), _iarr(flip), stream_ptr())
     return out
 
 
@@ -313,8 +371,9 @@ def blend_accumulate(logits, acc, profiles, origins):
     if logits is not None:
         assert logits.shape == (nwin, k, d, h, w) and logits.is_contiguous() and logits.dtype == torch.float32
     flat = [c for o in origins for c in o]
-    call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
-         _iarr(flat), stream_ptr(), launches=nwin)
+    with _hbm("blend_accumulate", nwin * k * d * h * w * (12.0 if logits is not None else 8.0)):
+        call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
+             _iarr(flat), stream_ptr(), launches=nwin)
 
 
 def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_before=None, apply_sigmoid=True,
@@ -322,9 +381,12 @@ def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_befor
     k, ad, ah, aw = acc.shape
     k2, vd, vh, vw = prob_sum.shape
     assert k == k2 and acc.is_contiguous() and prob_sum.is_contiguous()
-    call("b21_tta_accumulate", ptr(acc), ptr(cnt), ptr(prob_sum), k, ad, ah, aw,
-         _iarr(pad_before) if pad_before is not None else None, vd, vh, vw, _iarr(perm), _iarr(flip),
-         int(apply_sigmoid), int(overwrite), stream_ptr())
+    # acc read + prob_sum read-modify-write (write only when overwriting); the count map is read once per voxel
+    nb = k * vd * vh * vw * (8.0 if overwrite else 12.0) + (4.0 * vd * vh * vw if cnt is not None else 0.0)
+    with _hbm("tta_accumulate", nb):
+        call("b21_tta_accumulate", ptr(acc), ptr(cnt), ptr(prob_sum), k, ad, ah, aw,
+             _iarr(pad_before) if pad_before is not None else None, vd, vh, vw, _iarr(perm), _iarr(flip),
+             int(apply_sigmoid), int(overwrite), stream_ptr())
 
 
 def labels_finalize(prob_sum, count, thresh=0.5, image=None, want_onehot=True, want_label=True, et_label=4):
@@ -337,8 +399,9 @@ def labels_finalize(prob_sum, count, thresh=0.5, image=None, want_onehot=True, w
     if image is not None:
         assert image.dtype == torch.float32 and image.is_contiguous() and image.shape[-3:] == (vd, vh, vw)
         ic = image.shape[-4]
-    call("b21_labels_finalize", ptr(prob_sum), float(count), float(thresh), ptr(image), ic, ptr(onehot), ptr(label),
-         nvox, et_label, stream_ptr())
+    with _hbm("labels_finalize", nvox * (12.0 + 4.0 * ic + (3.0 if want_onehot else 0.0) + (1.0 if want_label else 0.0))):
+        call("b21_labels_finalize", ptr(prob_sum), float(count), float(thresh), ptr(image), ic, ptr(onehot), ptr(label),
+             nvox, et_label, stream_ptr())
     return onehot, label
 
 

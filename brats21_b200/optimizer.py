@@ -20,8 +20,12 @@ from ._lib import call, ptr, stream_ptr
 
 class Ranger2020(Optimizer):
     def __init__(self, params, lr=1e-3, alpha=0.5, k=6, N_sma_threshhold=5, betas=(.95, 0.999), eps=1e-5,
-                 weight_decay=0, use_gc=False, gc_conv_only=False, gc_loc=True, use_gcnorm=False, normloss_active=False,
-                 normloss_factor=1e-4):
+                 weight_decay=0, use_gc=True, use_gcnorm=False, normloss=False, normloss_factor=1e-4,
+                 gc_conv_only=False, gc_loc=True, normloss_active=None):
+        """Same positional order, keyword names and defaults as learning/optimizer.py:62-78 (``use_gc=True``,
+        ``normloss=``); ``normloss_active`` is kept as an alias of ``normloss``."""
+        if normloss_active is not None:
+            normloss = normloss_active
         if not 0.0 <= alpha <= 1.0:
             raise ValueError(f'Invalid slow update rate: {alpha}')
         if not 1 <= k:
@@ -30,19 +34,24 @@ class Ranger2020(Optimizer):
             raise ValueError(f'Invalid Learning Rate: {lr}')
         if not eps > 0:
             raise ValueError(f'Invalid eps: {eps}')
-        if use_gcnorm or normloss_active or (use_gc and not gc_loc):
+        if use_gcnorm or normloss or (use_gc and not gc_loc):
             raise NotImplementedError("gradient normalisation / norm loss / post-moment centralisation are off in "
                                       "the reference recipe (README.md:103-121) and not on the fused path")
-        defaults = dict(lr=lr, alpha=alpha, k=k, step_counter=0, betas=betas, N_sma_threshhold=N_sma_threshhold, eps=eps,
+        defaults = dict(lr=lr, alpha=alpha, k=k, betas=betas, N_sma_threshhold=N_sma_threshhold, eps=eps,
                         weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.N_sma_threshhold, self.alpha, self.k = N_sma_threshhold, alpha, k
-        self.use_gc, self.gc_conv_only = use_gc, gc_conv_only
+        self.use_gc, self.gc_conv_only, self.gc_loc, self.use_gcnorm = use_gc, gc_conv_only, gc_loc, use_gcnorm
+        self.normloss_active, self.normloss_factor, self.eps = normloss, normloss_factor, eps
         self.grad_scale = 1.0
         self._tables = {}
 
     def _table(self, gi, plist):
-        key = (gi, tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist))
+        # the device table stores raw pointers to the parameter, its gradient AND its three state tensors: all of
+        # them are part of the key (Optimizer.load_state_dict replaces the state tensors without touching p / p.grad)
+        key = (gi, self.use_gc, self.gc_conv_only,
+               tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                      self.state[p]["exp_avg_sq"].data_ptr(), self.state[p]["slow_buffer"].data_ptr()) for p in plist))
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
             return hit[1:]
@@ -107,4 +116,15 @@ class Ranger2020(Optimizer):
             call("b21_ranger_step", ptr(table), ptr(ctab), ctab.shape[0], float(self.grad_scale), float(group["lr"]),
                  float(step_size), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
                  int(rect), int(step % group["k"] == 0), float(self.alpha), stream_ptr())
+            # the kernel wrote the parameters through raw pointers: tell autograd / the packed-weight caches
+            # (networks._B21Net._ensure_packed keys on ``_version``) that they changed in place
+            torch._C._increment_version(plist)
         return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}

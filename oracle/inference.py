@@ -103,7 +103,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     x = F.pad(inputs, pad=pad, mode="constant", value=cval)
     origins = window_grid(image_size, roi, overlap)
     roi_v = tuple(min(i, r) for i, r in zip(image_size, roi))
-    wmap = importance_map(roi_v, mode, sigma_scale)
+    wmap = importance_map(roi_v, mode, sigma_scale).to(inputs.device)
     total = len(origins) * nb
     out = cnt = None
     for g0 in range(0, total, sw_batch_size):
@@ -117,7 +117,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
             prob = prob[0]
         prob = prob.float()
         if out is None:
-            out = torch.zeros((nb, prob.shape[1]) + image_size, dtype=torch.float32)
+            out = torch.zeros((nb, prob.shape[1]) + image_size, dtype=torch.float32, device=prob.device)
             cnt = torch.zeros_like(out)
         for j, idx in enumerate(idxs):
             b, o = idx // len(origins), origins[idx % len(origins)]
@@ -226,7 +226,7 @@ def brats_label_map(onehot: torch.Tensor, et_label: int = 4) -> torch.Tensor:
     Channels are (TC, WT, ET); result uint8 [1,1,D,H,W] with NCR/NET=1, ED=2, ET=4."""
     assert onehot.dim() == 5 and onehot.shape[0] == 1 and onehot.shape[1] == 3
     tc, wt, et = onehot[0, 0].bool(), onehot[0, 1].bool(), onehot[0, 2].bool()
-    lab = torch.zeros(tc.shape, dtype=torch.uint8)
+    lab = torch.zeros(tc.shape, dtype=torch.uint8, device=onehot.device)
     lab[et] = 3
     lab[tc & ~et] = 1
     lab[wt & ~tc] = 2

@@ -203,6 +203,21 @@ class Randomizable:
         raise NotImplementedError
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def eval_mode(*nets):
+    """monai.networks.utils.eval_mode (learning/engine.py:18,226): no_grad + .eval(), training flags restored."""
+    training = [n for n in nets if n.training]
+    try:
+        with torch.no_grad():
+            yield [n.eval() for n in nets]
+    finally:
+        for n in training:
+            n.train()
+
+
 def install():
     """Inject the shim as `monai` into sys.modules (idempotent)."""
     if "monai" in sys.modules and getattr(sys.modules["monai"], "__b21_shim__", False):
@@ -225,5 +240,6 @@ def install():
                                 ChannelSELayer=ChannelSELayer)
     monai.networks.layers = mod("monai.networks.layers", same_padding=same_padding, Act=Act, Conv=Conv)
     monai.networks.layers.factories = mod("monai.networks.layers.factories", Act=Act, Conv=Conv)
+    monai.networks.utils = mod("monai.networks.utils", eval_mode=eval_mode)
     monai.transforms = mod("monai.transforms")
     monai.transforms.compose = mod("monai.transforms.compose", Randomizable=Randomizable)

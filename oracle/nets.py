@@ -6,8 +6,8 @@ Functional restatement (plain torch fp32 ops over a reference-format ``state_dic
                                                               ConvEvoBlockCorrected/ConvEvo :192-222)
 plus the MONAI 0.6.0 blocks they use (MaxAvgPool, ResidualSELayer).
 
-Pinned against the unmodified reference modules by tests/test_oracle_vs_reference.py (in the build container) and
-against tests/golden/*.npz (everywhere).  MONAI-derived pieces remain "parity unpinned" (source not vendored).
+Pinned against the unmodified reference modules through tests/golden/*.npz (produced by tests/golden/make_golden.py
+from the unmodified reference; checked by tests/test_oracle_golden.py everywhere).  MONAI-derived pieces remain "parity unpinned" (source not vendored).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
 from __future__ import annotations

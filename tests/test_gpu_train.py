@@ -270,13 +270,13 @@ def test_ranger_step_matches_oracle():
     params = [torch.randn(s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
     ref_p = [p.detach().clone() for p in params]
     states = [otrain.RangerState(p) for p in ref_p]
-    opt = Ranger2020(params, lr=3e-4, weight_decay=1e-5)
+    opt = Ranger2020(params, lr=3e-4, weight_decay=1e-5, use_gc=False)
     for step in range(14):  # crosses the N_sma threshold (step 6) and two look-ahead syncs (6, 12)
         grads = [torch.randn(s, device=DEV, generator=g) for s in shapes]
         for p, gr in zip(params, grads):
             p.grad = gr.clone()
         opt.step()
-        otrain.ranger_step(ref_p, grads, states, lr=3e-4, weight_decay=1e-5)
+        otrain.ranger_step(ref_p, grads, states, lr=3e-4, weight_decay=1e-5, use_gc=False)
         for p, r in zip(params, ref_p):
             assert torch.allclose(p.detach(), r, rtol=2e-5, atol=2e-6), f"step {step + 1}"
 
@@ -397,7 +397,7 @@ def _ddp_worker(rank, world, port, out):
         net.load_state_dict(params)
         net.train()
         ddp = parallel.DistributedDataParallel(net, bucket_cap_mb=0.25)
-        opt = ddp.attach_optimizer(Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=1e-3))
+        opt = ddp.attach_optimizer(Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=1e-3, use_gc=False))
         tgt = synth.target(shape=(32, 32, 32)).to(DEV)
         x = synth.volume(seed=10 + rank, shape=(32, 32, 32)).to(DEV)
         ddp.zero_grad()
@@ -451,3 +451,104 @@ def test_data_parallel_gradients_are_rank_sums():
         f = net.grad_store().flat.clone()
         total = f if total is None else total + f
     assert _rel(g0.to(DEV), total) < 1e-2  # atomics order differs run to run and bf16 roundings amplify it
+
+
+def test_two_training_steps_packed_weights_follow_the_optimizer():
+    """The fused Ranger step updates the fp32 parameters through raw pointers; the packed bf16 conv weights (forward,
+    data-gradient packings, and the buffers captured by the inference CUDA graphs) must follow.  After one step with a
+    large learning rate the second forward — training mode, eval mode, and a graph captured BEFORE the step — is
+    compared with the oracle evaluated on the UPDATED parameters."""
+    from brats21_b200 import engine, networks
+    from brats21_b200.losses import DiceLoss
+    from brats21_b200.optimizer import Ranger2020
+    from oracle import nets, synth
+    width = 16
+    params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = networks.EquiUnetASSPEvo(4, 3, [width * 2 ** i for i in range(4)], deep_supervision=True).to(DEV)
+    net.load_state_dict(params)
+    x = synth.volume(seed=3, shape=(32, 32, 32)).to(DEV)
+    tgt = synth.target(shape=(32, 32, 32)).to(DEV)
+    net.eval()
+    with torch.no_grad():
+        x8 = net.pack_input(x)
+        before_graph = net.forward_infer(x8).clone()  # captures the inference graph on the initial weights
+    net.train()
+    opt = Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=1e-3, use_gc=False)
+    crit = DiceLoss()
+    versions = [p._version for p in net.parameters()]
+    # step 1 by hand so that the learning rate can be sized to move the largest conv weight by ~20 % (first Ranger
+    # step is un-rectified: p -= lr * g)
+    net.zero_grad()
+    _, loss1 = engine.compute_loss(None, crit, net(x), tgt)
+    loss1.backward()
+    ratio = max((p.grad.norm() / p.norm()).item() for n, p in net.named_parameters() if n.endswith("0.weight"))
+    opt.param_groups[0]["lr"] = 0.2 / ratio
+    opt.step()
+    assert all(p._version > v for p, v in zip(net.parameters(), versions) if p.grad is not None)
+    new_params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    moved = max(_rel(new_params[k], params[k]) for k in params if k.endswith("0.weight"))
+    assert moved > 0.1  # the step really changed the conv weights
+    with torch.no_grad():
+        ref_old, _ = nets.equiunet_v2_forward(params, x)
+        ref_new, _ = nets.equiunet_v2_forward(new_params, x)
+    sens = _rel(ref_new, ref_old)
+    assert sens > 0.06  # ... enough for stale packed weights to show
+    out2 = net(x)[0].detach()  # training-mode forward of step 2
+    assert _rel(out2, ref_new) < 3e-2 and _rel(out2, ref_old) > 0.5 * sens, (_rel(out2, ref_new), _rel(out2, ref_old))
+    net.eval()
+    with torch.no_grad():
+        assert _rel(net(x)[0], ref_new) < 3e-2
+        after_graph = net.forward_infer(x8)  # replay of the graph captured before the step
+        assert len(net._graphs) == 1
+        assert _rel(after_graph, ref_new) < 3e-2 and _rel(after_graph, before_graph) > 0.5 * sens
+    net.train()
+    loss2 = engine.train_step(None, net, crit, opt, x, tgt)  # the dgrad (.T) packings were refreshed too:
+    assert torch.isfinite(loss2)
+    got = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    ps = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith("running_var"))
+          for k, v in new_params.items()}
+    from oracle import train as otrain
+    out, deeps = nets.equiunet_v2_forward(ps, x)
+    otrain.deep_supervision_loss([out] + list(deeps), tgt, False).backward()
+    worst = {k: _rel(got[k], v.grad) for k, v in ps.items() if v.grad is not None}
+    assert max(worst.values()) < 0.15, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_ranger_state_reload_rebuilds_the_pointer_table():
+    """Optimizer.load_state_dict replaces exp_avg / exp_avg_sq / slow_buffer: the fused step must use the NEW tensors
+    (its device table caches raw pointers)."""
+    from brats21_b200.optimizer import Ranger2020
+    from oracle import train as otrain
+    g = torch.Generator(device=DEV).manual_seed(21)
+    shapes = [(24, 8, 3, 3, 3), (24,), (5000,)]
+    params = [torch.randn(s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
+    ref_p = [p.detach().clone() for p in params]
+    states = [otrain.RangerState(p) for p in ref_p]
+    opt = Ranger2020(params, lr=1e-3, weight_decay=1e-5, use_gc=False)
+
+    def one_step():
+        grads = [torch.randn(s, device=DEV, generator=g) for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone() if p.grad is None else p.grad.copy_(gr)
+        opt.step()
+        otrain.ranger_step(ref_p, grads, states, lr=1e-3, weight_decay=1e-5)
+
+    for _ in range(3):
+        one_step()
+    import copy
+    sd = copy.deepcopy(opt.state_dict())
+    for _ in range(2):  # diverge from the snapshot, then roll both sides back to it
+        one_step()
+    snap_p = None
+    opt.load_state_dict(sd)
+    for p, st in zip(params, states):
+        st_new = opt.state[p]
+        st.step, st.exp_avg, st.exp_avg_sq = st_new["step"], st_new["exp_avg"].clone(), st_new["exp_avg_sq"].clone()
+        st.slow = st_new["slow_buffer"].clone()
+    del snap_p
+    for step in range(4):
+        one_step()
+        for p, r in zip(params, ref_p):
+            assert torch.allclose(p.detach(), r, rtol=2e-5, atol=2e-6), f"step {step + 1} after reload"

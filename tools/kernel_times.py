@@ -25,7 +25,7 @@ def main():
         net = cls(4, 3, feats, norm_layer="group", act="relu", deep_supervision=True).to(dev)
     if wl == "v2_train":
         net.train()
-        opt = Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=3e-4, weight_decay=1e-5)
+        opt = Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=3e-4, weight_decay=1e-5, use_gc=False)
         crit = DiceLoss()
         img = synth.volume(seed=2000, shape=(128, 128, 128)).to(dev)
         tgt = synth.target(shape=(128, 128, 128)).to(dev)
