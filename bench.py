@@ -328,17 +328,24 @@ def measure_train(args, dx: Dist, steps: int, warmup: int, seed: int = 93):
     host_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
     img_dev, tgt_dev = host_img.to(dev), host_tgt.to(dev)
 
-    def step_device():
+    # the public API of the step: engine.TrainStep = engine.train_step replayed from one CUDA graph per input shape
+    graphed = engine.TrainStep(model, crit, opt)
+
+    def step_eager():
+        opt.disable_graph_mode()
         return engine.train_step(None, model, crit, opt, img_dev, tgt_dev)
+
+    def step_device():
+        return graphed(img_dev, tgt_dev)
 
     def step_e2e():
         img = host_img.to(dev, non_blocking=True)
         tgt = host_tgt.to(dev, non_blocking=True)
-        loss = engine.train_step(None, model, crit, opt, img, tgt)
+        loss = graphed(img, tgt)
         host_loss.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for _ in range(warmup):
+    for _ in range(max(warmup, graphed.eager_warmup + 1)):
         step_device()
     l0 = _lib.launch_count
     ms = dx.timed(step_device, steps)
@@ -353,14 +360,18 @@ def measure_train(args, dx: Dist, steps: int, warmup: int, seed: int = 93):
         hooks = (gs.on_begin, gs.on_ready, gs.on_finish)
         nbuckets, grad_bytes = len(model._reducer.bounds), gs.flat.numel() * 4
         gs.on_begin = gs.on_ready = gs.on_finish = None
-        step_device()
-        ms_nocomm = dx.timed(step_device, steps)
+        nocomm = engine.TrainStep(model, crit, opt)
+        for _ in range(nocomm.eager_warmup + 1):
+            nocomm(img_dev, tgt_dev)
+        ms_nocomm = dx.timed(lambda: nocomm(img_dev, tgt_dev), steps)
         gs.on_begin, gs.on_ready, gs.on_finish = hooks
         comm = {"allreduce_bytes_per_step": grad_bytes, "buckets": nbuckets, "backend": "nccl",
                 "ms_per_step_without_allreduce": ms_nocomm / steps,
                 "exposed_comm_ms_per_step": max(ms - ms_nocomm, 0.0) / steps}
+    step_eager()
+    ms_eager = dx.timed(step_eager, steps)
     ops.conv_profile = []
-    step_device()
+    step_eager()
     torch.cuda.synchronize()
     prof, ops.conv_profile = ops.conv_profile, None
     conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
@@ -373,6 +384,8 @@ def measure_train(args, dx: Dist, steps: int, warmup: int, seed: int = 93):
     block = {"metric": "train patches/s (EquiUNet-ASPP-Evo, 128^3, batch 1/GPU)", "value": world * steps / (ms * 1e-3),
              "unit": "patches/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
              "scaling": "weak", "dtype": "bf16", "loss_after": loss_value,
+             "api": "brats21_b200.engine.TrainStep (engine.train_step replayed from one CUDA graph)",
+             "ms_per_step_eager": ms_eager / steps,
              "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": "patches/s", "ms_per_step": ms_e2e / steps,
                      "h2d_bytes_per_step": (host_img.numel() + host_tgt.numel()) * 4, "d2h_bytes_per_step": 4},
              "gpu_launches": launches, "comm": comm,

@@ -51,9 +51,10 @@ _SIGNATURES = {
     "b21_conv1x1_fwd_fold": [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp],
     "b21_affine_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_pack_windows": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "b21_blend_accumulate": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "b21_blend_accumulate": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],
     "b21_tta_accumulate": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp],
     "b21_labels_finalize": [_vp, _f, _f, _vp, _i, _vp, _vp, _i64, _i, _vp],
+    "b21_mask_background": [_vp, _i, _vp, _i, _i64, _vp],
     "b21_conv3d_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv_wgrad_march_supported": [_i, _i],
     "b21_conv3d_wgrad_march": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -67,7 +68,7 @@ _SIGNATURES = {
     "b21_dice_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _vp],
     "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp],
     "b21_ranger_chunk": [],
-    "b21_ranger_step": [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _f, _vp],
+    "b21_ranger_step": [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _f, _vp, _vp],
     "b21_grad_centralize": [_vp, _i, _vp],
     "b21_foreground_bbox": [_vp, _i, _i, _i, _i, _vp, _vp],
     "b21_nonzero_stats": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],

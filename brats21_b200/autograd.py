@@ -46,8 +46,14 @@ class GradStore:
         # data-parallel hooks (brats21_b200.parallel.BucketReducer): start of a backward, "gradients in
         # flat[0:offset] are final", end of the backward
         self.on_begin: Optional[Callable[[], None]] = None
-        self.on_ready: Optional[Callable[[int], None]] = None
+        self.on_ready: Optional[Callable[..., None]] = None
         self.on_finish: Optional[Callable[[], None]] = None
+        # Weight gradients run on a SIDE stream: dW of a layer only feeds the optimizer, while the data gradient and
+        # the HBM-bound norm / pool adjoints of the next layers are on the critical path.  The tensor-bound wgrad
+        # kernels (one persistent CTA per SM, ~200 KB of shared memory each) co-reside with the register-only
+        # element-wise kernels, so the two streams fill each other's idle pipes.
+        self.side: Optional[torch.cuda.Stream] = None
+        self._side_dirty = False
 
     def begin(self):
         """Bind .grad views; zero the buffer unless the caller is accumulating into existing gradients."""
@@ -59,13 +65,40 @@ class GradStore:
         if self.on_begin is not None:
             self.on_begin()
 
+    def on_side(self, fn: Callable[[], None]):
+        """Run ``fn`` (kernel launches that only write parameter gradients) on the side stream, ordered after
+        everything enqueued so far on the current stream."""
+        if not (ops.wgrad_side_stream and self.flat.is_cuda) or ops.conv_profile is not None:
+            fn()
+            return
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.flat.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            fn()
+        self._side_dirty = True
+
+    def _side_event(self):
+        if not self._side_dirty:
+            return ()
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return (ev,)
+
     def finish(self):
+        if self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_dirty = False
         if self.on_finish is not None:
             self.on_finish()
 
     def ready(self, name: str):
+        """Gradients up to and including ``name`` (backward-completion order) are final once the work enqueued so far
+        on the current AND the side stream has run."""
         if self.on_ready is not None:
-            self.on_ready(self.offsets[name] + self.views[name].numel())
+            self.on_ready(self.offsets[name] + self.views[name].numel(), self._side_event())
 
 
 # ================================================================================================ V2
@@ -212,11 +245,11 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
                   b2=pk[name + ".se.b2"], dw1=G[pre + "6.fc.0.weight"], db1=G[pre + "6.fc.0.bias"],
                   dw2=G[pre + "6.fc.2.weight"], db2=G[pre + "6.fc.2.bias"])
         evo_bwd(name + ".e1.g", name + ".e1.b", dy, t["z1"], t["st1"], dy, G[pre + "3.bias"], se=se)   # dy <- dz1
-        ops.conv3d_wgrad(t["a0"], dy, G[pre + "3.weight"])
+        gs.on_side(lambda: ops.conv3d_wgrad(t["a0"], dy, G[pre + "3.weight"]))
         da0 = B(name + ".da0", s, c)
         ops.conv3d(dy, pk[name + ".c1.T"], out=da0)
         evo_bwd(name + ".e0.g", name + ".e0.b", da0, t["z0"], t["st0"], da0, G[pre + "0.bias"])       # da0 <- dz0
-        ops.conv3d_wgrad(t["x"], da0, G[pre + "0.weight"])
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], da0, G[pre + "0.weight"]))
         if dx_out is not None:
             ops.conv3d(da0, pk[name + ".c0.T"], out=dx_out)
         gs.ready(pre + "0.bias")
@@ -224,7 +257,7 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
     def convevo_bwd(name, dy, dz, dx_out):
         t = tape[name]
         evo_bwd(name + ".g", name + ".b", dy, t["z"], t["st"], dz, G[name + ".conv.bias"])
-        ops.conv3d_wgrad(t["x"], dz, G[name + ".conv.weight"])
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dz, G[name + ".conv.weight"]))
         if dx_out is not None:
             ops.conv3d(dz, pk[name + ".T"], out=dx_out)
         gs.ready(name + ".conv.bias")
@@ -294,7 +327,7 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
     for i, dil in enumerate(net.aspp.dilations):
         dz = g_acat[..., i * q:(i + 1) * q]
         G[f"aspp.convs.{i}.bias"].add_(dz.float().sum(dim=(0, 1, 2, 3)))
-        ops.conv3d_wgrad(y4, dz, G[f"aspp.convs.{i}.weight"], dil=dil)
+        gs.on_side(lambda dz=dz, i=i, dil=dil: ops.conv3d_wgrad(y4, dz, G[f"aspp.convs.{i}.weight"], dil=dil))
         ops.conv3d(dz, pk[f"aspp.convs.{i}.T"], out=g_y4 if i == 0 else tmp4, dil=dil)
         if i > 0:
             ops.add_inplace(g_y4, tmp4)
@@ -458,7 +491,7 @@ def _backward_v1(net, tape, dout, ddeeps, gs: GradStore):
         t = tape[name]
         ops.norm_bwd(dy, t["z"], dy, t["st"], pk[name + ".g"], pk[name + ".b"], G[name + ".bn.weight"],
                      G[name + ".bn.bias"], GN, workspace=nbw)
-        ops.conv3d_wgrad(t["x"], dy, G[name + ".conv.weight"], dil=t["dil"])
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dy, G[name + ".conv.weight"], dil=t["dil"]))
         if dx_out is not None:
             ops.conv3d(dy, pk[name + ".T"], out=dx_out, dil=t["dil"])
         gs.ready(name + ".conv.weight")

@@ -12,7 +12,14 @@ constexpr int kRangerChunk = 16384;
 // table: int64 [ntensors][6] = {param, grad, exp_avg, exp_avg_sq, slow, numel}; chunks: int32 [nchunks][2] = {tensor, offset}
 __global__ void __launch_bounds__(256) ranger_step_kernel(const long long* __restrict__ table, const int* __restrict__ chunks,
                                                           float gscale, float lr_step, float beta1, float beta2,
-                                                          float eps, float wd, int rectified, int lookahead, float alpha) {
+                                                          float eps, float wd, int rectified, int lookahead, float alpha,
+                                                          const float* __restrict__ dyn) {
+  if (dyn) {  // step-dependent scalars from device memory: the launch can be replayed from a CUDA graph
+    lr_step = dyn[0];
+    rectified = dyn[1] != 0.f;
+    lookahead = dyn[2] != 0.f;
+    gscale = dyn[3];
+  }
   const int ti = chunks[blockIdx.x * 2], off = chunks[blockIdx.x * 2 + 1];
   const long long* row = table + size_t(ti) * 6;
   float* p = reinterpret_cast<float*>(row[0]) + off;
@@ -56,10 +63,10 @@ extern "C" int b21_ranger_chunk(void) { return kRangerChunk; }
 
 extern "C" int b21_ranger_step(const long long* table, const int* chunks, int nchunks, float gscale, float lr,
                                float step_size, float beta1, float beta2, float eps, float weight_decay,
-                               int rectified, int lookahead, float alpha, void* stream) {
+                               int rectified, int lookahead, float alpha, const float* dyn, void* stream) {
   B21_CHECK_ARG(table && chunks && nchunks > 0, "ranger_step: empty parameter table");
   ranger_step_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, chunks, gscale, step_size * lr, beta1, beta2, eps,
-                                                                weight_decay, rectified, lookahead, alpha);
+                                                                weight_decay, rectified, lookahead, alpha, dyn);
   B21_LAUNCH_CHECK("ranger_step_kernel");
   return B21_OK;
 }

@@ -70,6 +70,75 @@ def train_step(args, model, criterion, optimizer, image, target, scaler=None):
     return loss.detach()
 
 
+class TrainStep:
+    """``train_step`` replayed from ONE CUDA graph per input shape: zero_grad, bf16 weight re-pack, forward, Dice over
+    all heads, the hand-scheduled backward (weight gradients on their side stream, the data-parallel bucket
+    all-reduces on theirs), and the fused Ranger launch — ~450 launches, several memsets and the autograd bookkeeping
+    become one ``cudaGraphLaunch``.  The step-dependent optimizer scalars (rectified step size, look-ahead phase,
+    learning rate) are uploaded to a small device buffer before every replay (``Ranger2020.begin_graph_step``), so
+    schedulers keep working; image / target are copied into static buffers.
+
+        step = TrainStep(model, criterion, optimizer)
+        for batch in loader:
+            loss = step(batch["img"].cuda(non_blocking=True), batch["seg"].cuda(non_blocking=True))   # device scalar
+
+    The optimizer must be ``brats21_b200.optimizer.Ranger2020``.  Same arithmetic as ``train_step`` (same kernels in
+    the same order); ``tests/test_gpu_train.py::test_graphed_train_step_matches_eager`` pins that."""
+
+    def __init__(self, model, criterion, optimizer, args=None, eager_warmup: int = 2):
+        if not hasattr(optimizer, "begin_graph_step"):
+            raise TypeError("TrainStep needs brats21_b200.optimizer.Ranger2020 (device-resident step scalars)")
+        self.model, self.criterion, self.optimizer, self.args = model, criterion, optimizer, args
+        self.eager_warmup = max(int(eager_warmup), 1)
+        self._graphs = {}
+        self.eager_steps = 0
+
+    def _params(self):
+        return [p for g in self.optimizer.param_groups for p in g["params"]]
+
+    def _capture(self, image, target):
+        dev = image.device
+        img = torch.empty_like(image, dtype=torch.float32).contiguous()
+        tgt = torch.empty_like(target, dtype=torch.float32).contiguous()
+        torch.cuda.synchronize(dev)
+        self.optimizer.enable_graph_mode()
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops._lib.launch_count
+        try:
+            with torch.cuda.graph(graph):  # records only: nothing executes, no host state advances (graph mode)
+                loss = train_step(self.args, self.model, self.criterion, self.optimizer, img, tgt)
+        except Exception:
+            self.optimizer.disable_graph_mode()
+            raise
+        return (graph, img, tgt, loss, ops._lib.launch_count - l0)
+
+    def __call__(self, image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if not image.is_cuda:
+            raise RuntimeError("TrainStep runs on CUDA only (no CPU fallback)")
+        key = (tuple(image.shape), tuple(target.shape), image.device.index)
+        entry = self._graphs.get(key)
+        if entry is None or isinstance(entry, int):
+            done = entry or 0
+            if done < self.eager_warmup:
+                # the first steps of a shape run eagerly: optimizer state, workspaces, packed weights, NCCL
+                # communicators and kernel attributes must exist before a capture
+                self.optimizer.disable_graph_mode()
+                self._graphs[key] = done + 1
+                self.eager_steps += 1
+                return train_step(self.args, self.model, self.criterion, self.optimizer, image, target)
+            entry = self._graphs[key] = self._capture(image, target)
+        graph, img, tgt, loss, launches = entry
+        self.optimizer.enable_graph_mode()
+        img.copy_(image, non_blocking=True)
+        tgt.copy_(target, non_blocking=True)
+        self.optimizer.begin_graph_step()
+        graph.replay()
+        ops._lib.launch_count += launches
+        # the replayed optimizer launch wrote the parameters: packed-weight caches outside the graph key on _version
+        torch._C._increment_version(self._params())
+        return loss
+
+
 def apply_tta(args, model, img, tta_transforms: Optional[Compose]) -> List:
     """Drop-in Engine._apply_tta: list (one entry per variant) of de-augmented outputs moved to the CPU."""
     outs = []
@@ -149,10 +218,15 @@ def predict_case(models: Sequence, raw_image: torch.Tensor, tta_transforms: Opti
     """
     from . import postprocess, preprocess
     vol, meta = preprocess.crop_normalize_pad(raw_image, 8, remove_outliers=remove_outliers)
+    post = cleaning_areas_threshold is not None or replace_value_threshold is not None
+    # reference order (learning/engine.py:249-256): threshold -> post transforms -> remove_background_voxels; without
+    # post transforms the background mask is fused into the label pass
     _, label = predict_volume(models, vol, tta_transforms, True, roi_size, sw_batch_size, overlap, mode,
-                              logit_thresh=logit_thresh)
+                              logit_thresh=logit_thresh, remove_background=not post)
     if cleaning_areas_threshold is not None:
         label = postprocess.KeepLargestConnectedComponent(cleaning_areas_threshold)(label)
     if replace_value_threshold is not None:
         label = postprocess.ReplaceWithClosestValue(labels=[3], thresh=replace_value_threshold)(label)
+    if post:
+        label = ops.mask_background(label.contiguous(), vol[0])
     return postprocess.pad_back(label[0, 0], meta)

@@ -12,6 +12,7 @@ crop, the same CUDA blending).
 """
 from __future__ import annotations
 
+import collections
 import itertools
 import math
 from typing import Any, Callable, Dict, List, Sequence, Tuple, Union
@@ -90,7 +91,21 @@ def importance_profiles(roi: Sequence[int], mode: str, sigma_scale, device) -> L
     return out
 
 
-_count_cache: Dict[Tuple, torch.Tensor] = {}
+# One full-volume fp32 map per geometry: after CropForeground nearly every case has its own shape (and the axis
+# permutations of the TTA add more), so the cache is a small LRU rather than a per-process leak.
+_COUNT_CACHE_ENTRIES = 8
+_count_cache: "collections.OrderedDict[Tuple, torch.Tensor]" = collections.OrderedDict()
+
+
+def importance_floor(profiles) -> float:
+    """MONAI clamps the 3-D importance map at its smallest non-zero value (compute_importance_map).  The map is the
+    outer product of the profiles, so that value is the product of the per-axis smallest non-zero entries, and the clamp
+    only changes entries where some factor is exactly 0 — possible only when the 4-sigma truncation falls inside the
+    window (sigma_scale < 1/8).  Returns 0.0 (no clamp needed) when every profile is strictly positive."""
+    if all(bool((p > 0).all()) for p in profiles):
+        return 0.0
+    mins = [p[p > 0].min() for p in profiles]
+    return float((mins[0] * mins[1]) * mins[2])
 
 
 def count_map(image_size, roi, overlap, mode, sigma_scale, device) -> torch.Tensor:
@@ -101,9 +116,13 @@ def count_map(image_size, roi, overlap, mode, sigma_scale, device) -> torch.Tens
         cnt = torch.zeros((1,) + tuple(image_size), dtype=torch.float32, device=device)
         prof = importance_profiles(roi, mode, sigma_scale, device)
         origins = window_origins(image_size, roi, overlap)
+        floor = importance_floor(prof)
         for i in range(0, len(origins), 16):
-            ops.blend_accumulate(None, cnt, prof, origins[i:i + 16])
+            ops.blend_accumulate(None, cnt, prof, origins[i:i + 16], floor)
         _count_cache[key] = cnt
+        while len(_count_cache) > _COUNT_CACHE_ENTRIES:
+            _count_cache.popitem(last=False)
+    _count_cache.move_to_end(key)
     return _count_cache[key]
 
 
@@ -121,6 +140,7 @@ class WindowPlan:
         self.roi = tuple(min(i, r) for i, r in zip(self.image_size, roi))
         self.origins = window_origins(self.image_size, self.roi, overlap)
         self.profiles = importance_profiles(self.roi, mode, sigma_scale, device)
+        self.wfloor = importance_floor(self.profiles)
         self.count = count_map(self.image_size, self.roi, overlap, mode, sigma_scale, device)
 
 
@@ -142,7 +162,7 @@ def accumulate_windows(vol: torch.Tensor, vol_idx: int, net, plan: WindowPlan, s
         shifted = [tuple(o - p for o, p in zip(org, plan.pad_before)) for org in group]
         ops.pack_windows(vol, x8, shifted, perm=perm, flip=flip, vol_index=[vol_idx] * nb)
         logits = net.forward_infer(x8)
-        ops.blend_accumulate(logits, acc, plan.profiles, group)
+        ops.blend_accumulate(logits, acc, plan.profiles, group, plan.wfloor)
 
 
 def sliding_window_inference(
@@ -207,7 +227,7 @@ def sliding_window_inference(
                 acc = torch.zeros((nb, seg.shape[1]) + plan.image_size, dtype=torch.float32, device=inputs.device)
             for j, idx in enumerate(idxs):
                 b, o = idx // len(plan.origins), plan.origins[idx % len(plan.origins)]
-                ops.blend_accumulate(seg[j:j + 1], acc[b], plan.profiles, [o])
+                ops.blend_accumulate(seg[j:j + 1], acc[b], plan.profiles, [o], plan.wfloor)
     out = torch.empty((nb, acc.shape[1]) + plan.image_size0, dtype=torch.float32, device=inputs.device)
     for b in range(nb):
         ops.tta_accumulate(acc[b], plan.count, out[b], pad_before=plan.pad_before, apply_sigmoid=False, overwrite=True)
@@ -229,4 +249,4 @@ def _fast_multi_volume(vol, net, plan, sw_batch_size, acc):
         ops.pack_windows(vol, x8, shifted, vol_index=vidx)
         logits = net.forward_infer(x8)
         for j, (o, b) in enumerate(zip(group, vidx)):
-            ops.blend_accumulate(logits[j:j + 1], acc[b], plan.profiles, [o])
+            ops.blend_accumulate(logits[j:j + 1], acc[b], plan.profiles, [o], plan.wfloor)

@@ -276,6 +276,8 @@ use_graphs = True
 use_wgrad_march = True
 # persistent 1x1 kernel (conv_point.cu) for the shapes it supports
 use_point = True
+# weight gradients on a side stream, overlapped with the data-gradient chain (autograd.GradStore.on_side)
+wgrad_side_stream = True
 
 
 # ---------------------------------------------------------------------------------------------- norm / SE / pool
@@ -362,8 +364,9 @@ def pack_windows(vol, out, origins, perm=(0, 1, 2), flip=(0, 0, 0), vol_index=No
     return out
 
 
-def blend_accumulate(logits, acc, profiles, origins):
-    """acc [K, AD, AH, AW] += outer(profiles) * logits [B, K, d, h, w]; logits None -> count map (K = 1)."""
+def blend_accumulate(logits, acc, profiles, origins, wfloor: float = 0.0):
+    """acc [K, AD, AH, AW] += max(outer(profiles), wfloor) * logits [B, K, d, h, w], windows added in order;
+    logits None -> count map (K = 1)."""
     k, ad, ah, aw = acc.shape
     pd, ph, pw = profiles
     d, h, w = pd.numel(), ph.numel(), pw.numel()
@@ -373,7 +376,7 @@ def blend_accumulate(logits, acc, profiles, origins):
     flat = [c for o in origins for c in o]
     with _hbm("blend_accumulate", nwin * k * d * h * w * (12.0 if logits is not None else 8.0)):
         call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
-             _iarr(flat), stream_ptr(), launches=nwin)
+             _iarr(flat), float(wfloor), stream_ptr())
 
 
 def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_before=None, apply_sigmoid=True,
@@ -403,6 +406,15 @@ def labels_finalize(prob_sum, count, thresh=0.5, image=None, want_onehot=True, w
         call("b21_labels_finalize", ptr(prob_sum), float(count), float(thresh), ptr(image), ic, ptr(onehot), ptr(label),
              nvox, et_label, stream_ptr())
     return onehot, label
+
+
+def mask_background(label, image):
+    """In place: zero the uint8 label planes [..., D, H, W] where every channel of image [C, D, H, W] is 0."""
+    nvox = image[0].numel()
+    assert label.dtype == torch.uint8 and label.is_contiguous() and label.numel() % nvox == 0
+    assert image.dtype == torch.float32 and image.is_contiguous()
+    call("b21_mask_background", ptr(label), label.numel() // nvox, ptr(image), image.shape[0], nvox, stream_ptr())
+    return label
 
 
 # ---------------------------------------------------------------------------------------------- training step

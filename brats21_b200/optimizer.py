@@ -45,6 +45,7 @@ class Ranger2020(Optimizer):
         self.normloss_active, self.normloss_factor, self.eps = normloss, normloss_factor, eps
         self.grad_scale = 1.0
         self._tables = {}
+        self._dyn = self._dyn_buf = None
 
     def _table(self, gi, plist):
         # the device table stores raw pointers to the parameter, its gradient AND its three state tensors: all of
@@ -77,45 +78,98 @@ class Ranger2020(Optimizer):
         self._tables[gi] = (key, table, ctab, gc_rows)
         return table, ctab, gc_rows
 
+    def _plist(self, group):
+        plist = [p for p in group["params"] if p.grad is not None]
+        for p in plist:
+            if not p.is_cuda:
+                raise RuntimeError("brats21_b200.Ranger2020 runs on CUDA only (no CPU fallback)")
+            if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() \
+                    or not p.grad.is_contiguous():
+                raise RuntimeError("Ranger2020 fused step needs contiguous fp32 parameters and gradients")
+        return plist
+
+    def _advance(self, group, plist):
+        """Host side of a step (optimizer.py:196-217): per-tensor step counters, N_sma, rectification, step size."""
+        for p in plist:
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+                st["slow_buffer"] = p.detach().clone()
+            st["step"] += 1
+        step = self.state[plist[0]]["step"]
+        if any(self.state[p]["step"] != step for p in plist):
+            raise RuntimeError("fused Ranger2020 step expects all parameters of a group to share the step count")
+        beta1, beta2 = group["betas"]
+        beta2_t = beta2 ** step
+        n_sma_max = 2 / (1 - beta2) - 1
+        n_sma = n_sma_max - 2 * step * beta2_t / (1 - beta2_t)
+        rect = n_sma > self.N_sma_threshhold
+        if rect:
+            step_size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_sma_max - 4) * (n_sma - 2) / n_sma * n_sma_max /
+                                  (n_sma_max - 2)) / (1 - beta1 ** step)
+        else:
+            step_size = 1.0 / (1 - beta1 ** step)
+        return step_size, bool(rect), step % group["k"] == 0
+
+    # ---- CUDA-graph mode (engine.TrainStep): the step-dependent scalars live in device memory
+    _RING = 16
+
+    def enable_graph_mode(self):
+        """After this, ``step()`` only LAUNCHES (its scalars come from a device buffer, so the launch can be captured
+        and replayed) and ``begin_graph_step()`` — called eagerly before every replay — advances the host state and
+        uploads the scalars.  Parameters must already have gradients and state (run one eager step first)."""
+        if self._dyn_buf is None:
+            dev = self.param_groups[0]["params"][0].device
+            ng = len(self.param_groups)
+            self._dyn_buf = torch.zeros((ng, 4), dtype=torch.float32, device=dev)
+            self._dyn_host = torch.zeros((self._RING, ng, 4), dtype=torch.float32).pin_memory()
+            self._dyn_events = [None] * self._RING
+            self._dyn_slot = 0
+        self._dyn = self._dyn_buf
+
+    def disable_graph_mode(self):
+        self._dyn = None
+
+    def begin_graph_step(self):
+        slot = self._dyn_slot
+        self._dyn_slot = (slot + 1) % self._RING
+        if self._dyn_events[slot] is not None:
+            self._dyn_events[slot].synchronize()  # the upload that last used this pinned slot (RING steps ago)
+        host = self._dyn_host[slot]
+        for gi, group in enumerate(self.param_groups):
+            plist = self._plist(group)
+            if not plist:
+                host[gi].zero_()
+                continue
+            step_size, rect, look = self._advance(group, plist)
+            host[gi, 0], host[gi, 1], host[gi, 2], host[gi, 3] = step_size * group["lr"], float(rect), float(look), \
+                float(self.grad_scale)
+        self._dyn_buf.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._dyn_events[slot] = ev
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
+        dyn = getattr(self, "_dyn", None)
         for gi, group in enumerate(self.param_groups):
-            plist = [p for p in group["params"] if p.grad is not None]
+            plist = self._plist(group)
             if not plist:
                 continue
-            for p in plist:
-                if not p.is_cuda:
-                    raise RuntimeError("brats21_b200.Ranger2020 runs on CUDA only (no CPU fallback)")
-                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() \
-                        or not p.grad.is_contiguous():
-                    raise RuntimeError("Ranger2020 fused step needs contiguous fp32 parameters and gradients")
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p)
-                    st["exp_avg_sq"] = torch.zeros_like(p)
-                    st["slow_buffer"] = p.detach().clone()
-                st["step"] += 1
-            step = self.state[plist[0]]["step"]
-            if any(self.state[p]["step"] != step for p in plist):
-                raise RuntimeError("fused Ranger2020 step expects all parameters of a group to share the step count")
             beta1, beta2 = group["betas"]
-            beta2_t = beta2 ** step
-            n_sma_max = 2 / (1 - beta2) - 1
-            n_sma = n_sma_max - 2 * step * beta2_t / (1 - beta2_t)
-            rect = n_sma > self.N_sma_threshhold
-            if rect:
-                step_size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_sma_max - 4) * (n_sma - 2) / n_sma * n_sma_max /
-                                      (n_sma_max - 2)) / (1 - beta1 ** step)
+            if dyn is None:
+                step_size, rect, look = self._advance(group, plist)
             else:
-                step_size = 1.0 / (1 - beta1 ** step)
+                step_size, rect, look = 0.0, False, False  # overridden by dyn[gi] on the device
             table, ctab, gc_rows = self._table(gi, plist)
             if gc_rows is not None:
                 call("b21_grad_centralize", ptr(gc_rows), gc_rows.shape[0], stream_ptr())
             call("b21_ranger_step", ptr(table), ptr(ctab), ctab.shape[0], float(self.grad_scale), float(group["lr"]),
                  float(step_size), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-                 int(rect), int(step % group["k"] == 0), float(self.alpha), stream_ptr())
+                 int(rect), int(look), float(self.alpha), ptr(dyn[gi]) if dyn is not None else None, stream_ptr())
             # the kernel wrote the parameters through raw pointers: tell autograd / the packed-weight caches
             # (networks._B21Net._ensure_packed keys on ``_version``) that they changed in place
             torch._C._increment_version(plist)

@@ -43,21 +43,24 @@ class BucketReducer:
     def start(self):
         self.next = 0
 
-    def _launch(self, lo: int, hi: int):
+    def _launch(self, lo: int, hi: int, after=()):
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(ev)
+                for e in after:  # e.g. the weight-gradient side stream of the backward
+                    self.comm.wait_event(e)
                 dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         else:
             dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
         self.launched += 1
 
-    def progress(self, final_upto: int):
-        """Gradients in flat[0:final_upto] are final (already enqueued on the current stream)."""
+    def progress(self, final_upto: int, after=()):
+        """Gradients in flat[0:final_upto] are final once the work already enqueued on the current stream (and the
+        CUDA events in ``after``) has completed."""
         while self.next < len(self.bounds) and self.bounds[self.next][1] <= final_upto:
-            self._launch(*self.bounds[self.next])
+            self._launch(*self.bounds[self.next], after=after)
             self.next += 1
 
     def finish(self):

@@ -177,12 +177,13 @@ int b21_head_conv(const void* x, int ldx, const float* scale, const float* offse
 int b21_pack_windows(const float* vol, int vc, int vd, int vh, int vw, void* out, int cpad, int nwin, int d, int h,
                      int w, const int* origins, const int* vol_index, const int* perm, const int* flip, void* stream);
 
-/* acc[k][ad][ah][aw] (+)= prof_d[z]*prof_h[y]*prof_w[x] * logits[win][k][z][y][x] for each window
- * (utils/inferers.py:149-151; importance map = outer product of the three 1-D profiles).  logits == NULL
- * accumulates the weights themselves (the count map, k = 1). */
+/* acc[k][ad][ah][aw] (+)= max(prof_d[z]*prof_h[y]*prof_w[x], wfloor) * logits[win][k][z][y][x] for each of the nwin
+ * (<= 16) windows, added in window order (utils/inferers.py:149-151; importance map = outer product of the three 1-D
+ * profiles, clamped below at its smallest non-zero value `wfloor` as MONAI's compute_importance_map does; 0 = no
+ * clamp).  logits == NULL accumulates the weights themselves (the count map, k = 1). */
 int b21_blend_accumulate(const float* logits, float* acc, const float* prof_d, const float* prof_h,
                          const float* prof_w, int nwin, int k, int d, int h, int w, int ad, int ah, int aw,
-                         const int* origins, void* stream);
+                         const int* origins, float wfloor, void* stream);
 
 /* prob_sum[k][vd][vh][vw] (+)= sigmoid(acc/cnt) de-augmented (inferers.py:154-162 + deaugment_mask +
  * engine.py:239-249).  cnt may be NULL; pad_before = the F.pad offsets of the augmented frame (or NULL). */
@@ -195,6 +196,12 @@ int b21_tta_accumulate(const float* acc, const float* cnt, float* prob_sum, int 
  * (ConvertToBratsClassesBasedOnMultiChannel + ChangeLabel3To4, utils/transforms.py:169-206). */
 int b21_labels_finalize(const float* prob_sum, float count, float thresh, const float* image, int image_channels,
                         uint8_t* onehot, uint8_t* label, long long nvox, int et_label, void* stream);
+
+/* remove_background_voxels (utils/transforms.py:536-550) as its own pass, for the flows where the reference runs the
+ * post transforms between the threshold and the background mask (learning/engine.py:249-256): label planes
+ * uint8 [planes][nvox] are zeroed where every channel of image fp32 [image_channels][nvox] is exactly 0. */
+int b21_mask_background(uint8_t* label, int planes, const float* image, int image_channels, long long nvox,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------- training step
  * Backward of the network body and the criterion (learning/engine.py:88-130: forward, Dice over the heads,
@@ -256,11 +263,13 @@ int b21_dice_bwd(const float* logits, const float* target, const float* coef, co
 
 /* Fused multi-tensor Ranger2020 step (learning/optimizer.py:136-255).  table: int64 [ntensors][6] = {param, grad,
  * exp_avg, exp_avg_sq, slow_buffer (device pointers, fp32), numel}; chunks: int32 [nchunks][2] = {tensor, offset}
- * with b21_ranger_chunk() elements per chunk; gscale multiplies every gradient (loss-scale / data-parallel mean). */
+ * with b21_ranger_chunk() elements per chunk; gscale multiplies every gradient (loss-scale / data-parallel mean).
+ * dyn (optional, device float[4] = {lr * step_size, rectified, lookahead, gscale}) overrides the step-dependent scalar
+ * arguments at run time, so that one captured launch serves every step of a CUDA-graphed training loop. */
 int b21_ranger_chunk(void);
 int b21_ranger_step(const long long* table, const int* chunks, int nchunks, float gscale, float lr, float step_size,
                     float beta1, float beta2, float eps, float weight_decay, int rectified, int lookahead, float alpha,
-                    void* stream);
+                    const float* dyn, void* stream);
 
 /* Gradient centralisation (centralized_gradient, learning/optimizer.py:11-20, applied at optimizer.py:187-188 when
  * use_gc): every dim-0 slice of a qualifying gradient tensor has its mean subtracted in place, before

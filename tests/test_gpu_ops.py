@@ -340,3 +340,48 @@ def test_pack_blend_tta_labels_bit_exact():
     hard = oinf.remove_background_voxels(img[None].cpu(), hard)
     assert torch.equal(onehot.cpu().float()[None], hard)
     assert torch.equal(label.cpu()[None, None], oinf.brats_label_map(hard))
+
+
+def test_blend_and_tta_vectorised_paths():
+    """float4 paths (x extents / origins multiples of 4; flip-only variants): blending bit-exact in the reference's
+    window order, de-augmentation against torch flips, and MONAI's importance-map floor for sigma_scale < 1/8."""
+    from brats21_b200 import inferers, ops
+    from oracle import inference as oinf
+    g = torch.Generator(device=DEV).manual_seed(17)
+    prof = [torch.rand(8, device=DEV, generator=g) + 0.1 for _ in range(3)]
+    logits = torch.randn((4, 3, 8, 8, 8), device=DEV, generator=g)
+    acc = torch.randn((3, 16, 12, 16), device=DEV, generator=g)
+    ref = acc.clone()
+    origins = [(0, 0, 0), (0, 4, 4), (8, 4, 8), (6, 3, 4)]  # overlapping, all x origins multiples of 4
+    ops.blend_accumulate(logits, acc, prof, origins)
+    wmap = prof[0].reshape(-1, 1, 1) * prof[1].reshape(1, -1, 1) * prof[2].reshape(1, 1, -1)
+    for j, o in enumerate(origins):
+        ref[:, o[0]:o[0] + 8, o[1]:o[1] + 8, o[2]:o[2] + 8] += wmap * logits[j]
+    assert torch.equal(acc, ref)
+    # every flip subset, padded augmented frame, accumulate and overwrite
+    a = torch.randn((3, 14, 12, 24), device=DEV, generator=g)
+    cnt = torch.rand((1, 14, 12, 24), device=DEV, generator=g) + 0.5
+    for bits in range(8):
+        flip = (bits & 1, (bits >> 1) & 1, (bits >> 2) & 1)
+        ps = torch.full((3, 12, 10, 16), 0.5, device=DEV)
+        ops.tta_accumulate(a, cnt, ps, (0, 1, 2), flip, pad_before=(1, 2, 4))
+        core = torch.sigmoid(a / cnt)[:, 1:13, 2:12, 4:20]
+        dims = [i + 1 for i in range(3) if flip[i]]
+        want = 0.5 + (core.flip(dims) if dims else core)
+        assert torch.allclose(ps, want, rtol=1e-6, atol=1e-6), flip
+        ops.tta_accumulate(a, cnt, ps, (0, 1, 2), flip, pad_before=(1, 2, 4), apply_sigmoid=False, overwrite=True)
+        core = (a / cnt)[:, 1:13, 2:12, 4:20]
+        assert torch.equal(ps, core.flip(dims) if dims else core), flip
+    # sigma_scale 0.05 on a 32-voxel window: the truncated Gaussian has zeros inside the window; MONAI clamps the 3-D
+    # map at its smallest non-zero value, so the count map stays positive and out/count finite
+    roi, img = (32, 32, 32), (40, 32, 48)
+    plan = inferers.WindowPlan(img, roi, 0.25, "gaussian", 0.05, torch.device(DEV))
+    assert plan.wfloor > 0 and plan.count.min().item() > 0
+    wm = oinf.importance_map(roi, "gaussian", 0.05).to(DEV)
+    want = torch.zeros((1,) + img, device=DEV)
+    for o in plan.origins:
+        want[:, o[0]:o[0] + 32, o[1]:o[1] + 32, o[2]:o[2] + 32] += wm
+    assert torch.allclose(plan.count, want, rtol=1e-6, atol=1e-30)
+    x = torch.randn((1, 3) + img, device=DEV, generator=g)
+    y = inferers.sliding_window_inference(x, roi, 2, lambda z: z, overlap=0.25, mode="gaussian", sigma_scale=0.05)
+    assert torch.isfinite(y).all() and (y - x).abs().max().item() <= 1e-5

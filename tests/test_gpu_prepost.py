@@ -202,8 +202,19 @@ def test_predict_case_end_to_end_matches_oracle_chain():
     p = plain.cpu().numpy()
     assert np.array_equal(p[mfull], full[mfull])
     assert p[~np.any(raw != 0, axis=0)].max() == 0  # background removed, zero outside the crop box
-    # the cleaned result equals the oracle's component filter applied to OUR un-cleaned map (integer stage: exact)
-    assert np.array_equal(got.cpu().numpy(), pp.get_largest_component(p, 10))
+    # reference order (learning/engine.py:249-256): threshold -> post transforms -> remove_background_voxels.  The
+    # cleaned result equals the oracle's component filter applied to OUR un-masked label map, then the background
+    # mask, then the pad-back (integer stages: exact)
+    from brats21_b200 import preprocess
+    vol_d, meta = preprocess.crop_normalize_pad(torch.from_numpy(raw).to(DEV), 8)
+    _, nobg = engine.predict_volume([net], vol_d, tta.get_flip8_transforms(), True, (32, 32, 32), 2,
+                                    remove_background=False)
+    cleaned = pp.get_largest_component(nobg[0, 0].cpu().numpy(), 10)
+    cleaned[~np.any(vol_d[0].cpu().numpy() != 0, axis=0)] = 0
+    want = np.zeros(raw.shape[1:], dtype=np.uint8)
+    want[start[0]:end[0], start[1]:end[1], start[2]:end[2]] = \
+        cleaned[pb[0]:lab.shape[0] - pa[0], pb[1]:lab.shape[1] - pa[1], pb[2]:lab.shape[2] - pa[2]]
+    assert np.array_equal(got.cpu().numpy(), want)
 
 
 def test_post_transforms_factory_with_cleaning():

@@ -378,7 +378,7 @@ def test_v1_training_step_matches_oracle():
     assert not bad, f"gradient error beyond torch-autocast's own: {sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]}"
 
 
-def _ddp_worker(rank, world, port, out):
+def _ddp_worker(rank, world, port, out, backend="gloo"):
     import os
     import torch.distributed as dist
     from brats21_b200 import engine, networks, parallel
@@ -386,9 +386,14 @@ def _ddp_worker(rank, world, port, out):
     from brats21_b200.optimizer import Ranger2020
     from oracle import synth
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0 (NCCL needs distinct GPUs)
+    # gloo: both ranks share cuda:0 (NCCL needs distinct GPUs); nccl: one GPU per rank, the production path
+    dev_index = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_index)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev_index))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        torch.cuda.set_device(0)
         width = 16
         params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
         with warnings.catch_warnings():
@@ -414,10 +419,14 @@ def _ddp_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_data_parallel_gradients_are_rank_sums():
-    """world 2 (gloo, both ranks on cuda:0): the bucketed all-reduce leaves every rank with the SUM of the per-rank
-    gradients, the fused optimizer applies the 1/world mean, and the ranks stay bit-identical."""
+@pytest.mark.parametrize("backend", ["gloo", "nccl"])
+def test_data_parallel_gradients_are_rank_sums(backend):
+    """world 2 (gloo: both ranks on cuda:0; nccl: one GPU per rank over NVLink, needs >= 2 GPUs — run with
+    `gpurun --gpus 2`): the bucketed all-reduce leaves every rank with the SUM of the per-rank gradients, the fused
+    optimizer applies the 1/world mean, and the ranks stay bit-identical."""
     import socket
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("the NCCL data-parallel test needs two GPUs")
     import torch.multiprocessing as mp
     from brats21_b200 import engine, networks
     from brats21_b200.losses import DiceLoss
@@ -427,7 +436,7 @@ def test_data_parallel_gradients_are_rank_sums():
         port = s.getsockname()[1]
     with mp.Manager() as m:
         out = m.dict()
-        mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+        mp.spawn(_ddp_worker, args=(2, port, out, backend), nprocs=2, join=True)
         res = dict(out)
     (g0, p0, nb, launched), (g1, p1, _, _) = res[0], res[1]
     assert nb > 3 and launched == nb
@@ -552,3 +561,48 @@ def test_ranger_state_reload_rebuilds_the_pointer_table():
         one_step()
         for p, r in zip(params, ref_p):
             assert torch.allclose(p.detach(), r, rtol=2e-5, atol=2e-6), f"step {step + 1} after reload"
+
+
+def test_graphed_train_step_matches_eager():
+    """engine.TrainStep (one CUDA graph per step: re-pack, forward, loss, backward with the side-stream weight
+    gradients, fused Ranger with device-resident step scalars) against the eager engine.train_step on a twin network:
+    same kernels in the same order, so losses and parameters track each other across the un-rectified steps, the
+    rectification switch (step 6) and a look-ahead sync, with a learning-rate change in between."""
+    from brats21_b200 import engine, networks
+    from brats21_b200.losses import DiceLoss
+    from brats21_b200.optimizer import Ranger2020
+    from oracle import synth
+    width = 16
+
+    def fresh():
+        params = {k: v.to(DEV) for k, v in synth.make_params(2, width, 93).items()}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net = networks.EquiUnetASSPEvo(4, 3, [width * 2 ** i for i in range(4)], deep_supervision=True).to(DEV)
+        net.load_state_dict(params)
+        net.train()
+        opt = Ranger2020([p for n, p in net.named_parameters() if not n.endswith(".v")], lr=2e-3, weight_decay=1e-5,
+                         use_gc=False)
+        return net, opt
+
+    tgt = synth.target(shape=(32, 32, 32)).to(DEV)
+    xs = [synth.volume(seed=40 + i, shape=(32, 32, 32)).to(DEV) for i in range(9)]
+    net_e, opt_e = fresh()
+    net_g, opt_g = fresh()
+    step = engine.TrainStep(net_g, DiceLoss(), opt_g, eager_warmup=1)
+    crit = DiceLoss()
+    for i, x in enumerate(xs):
+        if i == 4:
+            for o in (opt_e, opt_g):
+                o.param_groups[0]["lr"] = 5e-4
+        le = engine.train_step(None, net_e, crit, opt_e, x, tgt).item()
+        lg = step(x, tgt).item()
+        assert abs(le - lg) <= 3e-3, (i, le, lg)
+    assert step.eager_steps == 1 and len(step._graphs) == 1 and not isinstance(next(iter(step._graphs.values())), int)
+    assert opt_g.state[next(iter(opt_g.state))]["step"] == len(xs)
+    for (n, p), q in zip(net_e.named_parameters(), net_g.parameters()):
+        assert _rel(q.detach(), p.detach()) <= 5e-3, n
+    # leaving the graph: eval-mode inference sees the weights of the last replayed step
+    net_g.eval(), net_e.eval()
+    with torch.no_grad():
+        assert _rel(net_g(xs[0])[0], net_e(xs[0])[0]) <= 2e-2
