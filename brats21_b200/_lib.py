@@ -66,7 +66,8 @@ _SIGNATURES = {
     "b21_head_conv_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp],
     "b21_add_inplace": [_vp, _i, _vp, _i, _i64, _i, _vp],
     "b21_dice_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _vp],
-    "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i64, _vp],
+    "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i64, _vp],
+    "b21_ce_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i64, _f, _vp],
     "b21_ranger_chunk": [],
     "b21_ranger_step": [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _i, _i, _f, _vp, _vp],
     "b21_grad_centralize": [_vp, _i, _vp],
@@ -133,7 +134,7 @@ def stream_ptr():
 
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
-             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2,
+             "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2, "b21_ce_fwd": 2,
              "b21_keep_components_workspace_bytes": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
              "b21_keep_components": 4, "b21_replace_rare_labels": 5}
 launch_count = 0

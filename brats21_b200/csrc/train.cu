@@ -96,10 +96,56 @@ __global__ void dice_finalize_kernel(const double* __restrict__ sums, float* __r
   atomicAdd(loss, float(acc / K) * weight);
 }
 
-// dlogits = gscale * (c_t t + c_p p) * p (1 - p)
+// Cross-entropy half of DiceCELoss (learning/losses.py:470-595): torch.nn.CrossEntropyLoss(reduction="mean") over the
+// K class logits of every voxel against y = argmax_k target (first maximum; `ce()` at losses.py:562-577).
+__device__ __forceinline__ int first_argmax(const float* t, int K) {
+  int y = 0;
+  float best = t[0];
+  for (int k = 1; k < K; ++k)
+    if (t[k] > best) { best = t[k]; y = k; }
+  return y;
+}
+
+constexpr int kMaxClasses = 16;
+
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                     double* __restrict__ sum, int N, int K, long long nvox) {
+  float acc = 0.f;
+  const long long total = (long long)N * nvox;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / nvox, v = i - n * nvox;
+    const float* x = logits + size_t(n) * K * nvox + v;
+    const float* t = target + size_t(n) * K * nvox + v;
+    float xs[kMaxClasses], ts[kMaxClasses];
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      xs[k] = x[size_t(k) * nvox];
+      ts[k] = t[size_t(k) * nvox];
+      m = fmaxf(m, xs[k]);
+    }
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(xs[k] - m);
+    acc += m + logf(se) - xs[first_argmax(ts, K)];
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += double(red[w]);
+    atomicAdd(sum, s);
+  }
+}
+
+__global__ void ce_finalize_kernel(const double* __restrict__ sum, float* __restrict__ loss, double count, float weight) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(loss, float(sum[0] / count) * weight);
+}
+
+// dlogits = gscale * [ (c_t t + c_p p) * p (1 - p)  +  ce_w * (softmax_k - [k == y]) ]
 __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                        const float* __restrict__ coef, const float* __restrict__ gout,
-                                                       float gscale, float* __restrict__ dlogits, int N, int K,
+                                                       float gscale, float ce_w, float* __restrict__ dlogits, int N, int K,
                                                        long long nvox) {
   const long long total = (long long)N * K * nvox;
   const float g = gscale * (gout ? __ldg(gout) : 1.f);
@@ -107,7 +153,21 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
     const int k = int((i / nvox) % K);
     const float p = 1.f / (1.f + expf(-logits[i]));
     const float t = target[i];
-    dlogits[i] = g * (__ldg(coef + 2 * k) * t + __ldg(coef + 2 * k + 1) * p) * p * (1.f - p);
+    float d = (__ldg(coef + 2 * k) * t + __ldg(coef + 2 * k + 1) * p) * p * (1.f - p);
+    if (ce_w != 0.f) {
+      const long long base = i - (long long)k * nvox;  // channel 0 of this voxel
+      float ts[kMaxClasses];
+      float m = -INFINITY;
+      for (int j = 0; j < K; ++j) {
+        ts[j] = target[base + (long long)j * nvox];
+        m = fmaxf(m, logits[base + (long long)j * nvox]);
+      }
+      float se = 0.f;
+      for (int j = 0; j < K; ++j) se += expf(logits[base + (long long)j * nvox] - m);
+      const float sm = expf(logits[i] - m) / se;
+      d += ce_w * (sm - (first_argmax(ts, K) == k ? 1.f : 0.f));
+    }
+    dlogits[i] = g * d;
   }
 }
 
@@ -706,12 +766,27 @@ extern "C" int b21_dice_fwd(const float* logits, const float* target, double* su
   return B21_OK;
 }
 
+extern "C" int b21_ce_fwd(const float* logits, const float* target, double* scratch, float* loss, int n, int k,
+                          long long nvox, float weight, void* stream) {
+  B21_CHECK_ARG(logits && target && scratch && loss, "ce_fwd: null pointer");
+  B21_CHECK_ARG(n > 0 && k > 1 && k <= kMaxClasses && nvox > 0, "ce_fwd: bad sizes (2..%d classes)", kMaxClasses);
+  cudaStream_t st = (cudaStream_t)stream;
+  B21_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  ce_fwd_kernel<<<grid_cap(((long long)n * nvox + 1023) / 1024, 4), 256, 0, st>>>(logits, target, scratch, n, k, nvox);
+  ce_finalize_kernel<<<1, 32, 0, st>>>(scratch, loss, double(n) * double(nvox), weight);
+  B21_LAUNCH_CHECK("ce_fwd_kernel");
+  return B21_OK;
+}
+
 extern "C" int b21_dice_bwd(const float* logits, const float* target, const float* coef, const float* gout, float gscale,
-                            float* dlogits, int n, int k, long long nvox, void* stream) {
+                            float ce_weight, float* dlogits, int n, int k, long long nvox, void* stream) {
   B21_CHECK_ARG(logits && target && coef && dlogits, "dice_bwd: null pointer");
+  B21_CHECK_ARG(ce_weight == 0.f || (k > 1 && k <= kMaxClasses), "dice_bwd: the cross-entropy term needs 2..%d classes", kMaxClasses);
   const long long total = (long long)n * k * nvox;
+  // ce_weight is d(total loss)/d(ce loss) = lambda_ce; the mean over n * nvox voxels is applied here
+  const float ce_w = ce_weight / float(double(n) * double(nvox));
   dice_bwd_kernel<<<grid_cap((total + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(logits, target, coef, gout, gscale,
-                                                                                      dlogits, n, k, nvox);
+                                                                                      ce_w, dlogits, n, k, nvox);
   B21_LAUNCH_CHECK("dice_bwd_kernel");
   return B21_OK;
 }

@@ -76,6 +76,10 @@ def make_criterion(args: argparse.Namespace):
         return DiceLoss(jaccard=False)
     if args.criterion == "jaccard":
         return DiceLoss(jaccard=True)
+    if args.criterion == "dice_ce":  # src/definer.py:204-212
+        from .losses import DiceCELoss
+        return DiceCELoss(include_background=True, sigmoid=True, softmax=False, squared_pred=True, batch=True,
+                          reduction="mean")
     raise NameError("Not Supported Criterion")
 
 

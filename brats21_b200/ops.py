@@ -529,9 +529,17 @@ def dice_fwd(logits, target, loss, jaccard=False, weight=1.0, smooth_nr=1e-5, sm
     return coef
 
 
-def dice_bwd(logits, target, coef, gout=None, gscale=1.0):
+def ce_fwd(logits, target, loss, weight=1.0):
+    """loss[0] += weight * CrossEntropy(logits, argmax_k target) (mean over batch and voxels)."""
+    n, k = logits.shape[:2]
+    scratch = torch.empty((1,), dtype=torch.float64, device=logits.device)
+    call("b21_ce_fwd", ptr(logits), ptr(target), ptr(scratch), ptr(loss), n, k, logits[0, 0].numel(), weight,
+         stream_ptr())
+
+
+def dice_bwd(logits, target, coef, gout=None, gscale=1.0, ce_weight=0.0):
     n, k = logits.shape[:2]
     dl = torch.empty_like(logits)
-    call("b21_dice_bwd", ptr(logits), ptr(target), ptr(coef), ptr(gout), gscale, ptr(dl), n, k, logits[0, 0].numel(),
-         stream_ptr())
+    call("b21_dice_bwd", ptr(logits), ptr(target), ptr(coef), ptr(gout), gscale, float(ce_weight), ptr(dl), n, k,
+         logits[0, 0].numel(), stream_ptr())
     return dl

@@ -259,7 +259,13 @@ int b21_add_inplace(void* dst, int ldd, const void* src, int lds, long long nvox
 int b21_dice_fwd(const float* logits, const float* target, double* sums, float* loss, float* coef, int n, int k,
                  long long nvox, int jaccard, float smooth_nr, float smooth_dr, float weight, void* stream);
 int b21_dice_bwd(const float* logits, const float* target, const float* coef, const float* gout, float gscale,
-                 float* dlogits, int n, int k, long long nvox, void* stream);
+                 float ce_weight, float* dlogits, int n, int k, long long nvox, void* stream);
+/* Cross-entropy half of DiceCELoss (learning/losses.py:470-595, `--criterion dice_ce`, src/definer.py:204-212):
+ * loss[0] += weight * mean over the n * nvox voxels of CrossEntropy(logits[:, :, v], argmax_k target[:, k, v])
+ * (first maximum, as torch.argmax at losses.py:572); scratch = one double.  Its gradient is folded into b21_dice_bwd:
+ * ce_weight = lambda_ce adds lambda_ce * (softmax_k - [k == y]) / (n * nvox) to the Dice term (0 = plain Dice). */
+int b21_ce_fwd(const float* logits, const float* target, double* scratch, float* loss, int n, int k, long long nvox,
+               float weight, void* stream);
 
 /* Fused multi-tensor Ranger2020 step (learning/optimizer.py:136-255).  table: int64 [ntensors][6] = {param, grad,
  * exp_avg, exp_avg_sq, slow_buffer (device pointers, fp32), numel}; chunks: int32 [nchunks][2] = {tensor, offset}

@@ -206,6 +206,43 @@ class Randomizable:
 import contextlib
 
 
+class DiceLoss(nn.Module):
+    """monai.losses.DiceLoss restated for the flag combinations the reference uses (src/definer.py:184-212; SURVEY.md
+    Appendix A): include_background=True, to_onehot_y=False, sigmoid / no activation, squared_pred, jaccard, batch,
+    reduction mean|sum|none."""
+
+    def __init__(self, include_background=True, to_onehot_y=False, sigmoid=False, softmax=False, other_act=None,
+                 squared_pred=False, jaccard=False, reduction="mean", smooth_nr=1e-5, smooth_dr=1e-5, batch=False):
+        super().__init__()
+        if to_onehot_y or softmax or other_act is not None or not include_background:
+            raise NotImplementedError("monai shim: DiceLoss flag combination not restated")
+        self.sigmoid, self.squared_pred, self.jaccard, self.batch = sigmoid, squared_pred, jaccard, batch
+        self.reduction = getattr(reduction, "value", reduction)
+        self.smooth_nr, self.smooth_dr = float(smooth_nr), float(smooth_dr)
+
+    def forward(self, input, target):  # noqa: A002
+        if self.sigmoid:
+            input = torch.sigmoid(input)  # noqa: A001
+        if target.shape != input.shape:
+            raise AssertionError(f"ground truth has differing shape ({target.shape}) from input ({input.shape})")
+        reduce_axis = list(range(2, input.dim()))
+        if self.batch:
+            reduce_axis = [0] + reduce_axis
+        intersection = torch.sum(target * input, dim=reduce_axis)
+        if self.squared_pred:
+            target = torch.pow(target, 2)
+            input = torch.pow(input, 2)  # noqa: A001
+        denominator = torch.sum(target, dim=reduce_axis) + torch.sum(input, dim=reduce_axis)
+        if self.jaccard:
+            denominator = 2.0 * (denominator - intersection)
+        f = 1.0 - (2.0 * intersection + self.smooth_nr) / (denominator + self.smooth_dr)
+        if self.reduction == "mean":
+            return torch.mean(f)
+        if self.reduction == "sum":
+            return torch.sum(f)
+        return f
+
+
 @contextlib.contextmanager
 def eval_mode(*nets):
     """monai.networks.utils.eval_mode (learning/engine.py:18,226): no_grad + .eval(), training flags restored."""
@@ -241,5 +278,7 @@ def install():
     monai.networks.layers = mod("monai.networks.layers", same_padding=same_padding, Act=Act, Conv=Conv)
     monai.networks.layers.factories = mod("monai.networks.layers.factories", Act=Act, Conv=Conv)
     monai.networks.utils = mod("monai.networks.utils", eval_mode=eval_mode)
+    monai.losses = mod("monai.losses", DiceLoss=DiceLoss)
+    monai.losses.dice = mod("monai.losses.dice", DiceLoss=DiceLoss)
     monai.transforms = mod("monai.transforms")
     monai.transforms.compose = mod("monai.transforms.compose", Randomizable=Randomizable)

@@ -119,8 +119,10 @@ def _install_import_stubs():
             setattr(self, name, v)
             return v
 
+    # consulted LAST on sys.meta_path, i.e. only for modules the image really lacks (sklearn and pandas exist in the
+    # build container but not on every GPU box)
     tops = {"SimpleITK", "skimage", "nibabel", "openpyxl", "oyaml", "tensorboard", "tensorboardX", "ranger21", "monai",
-            "matplotlib", "seaborn", "apex", "medpy"}
+            "matplotlib", "seaborn", "apex", "medpy", "sklearn", "pandas", "scipy", "yaml", "tqdm"}
 
     class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         def find_spec(self, name, path, target=None):

@@ -28,6 +28,15 @@ def dice_loss(logits: torch.Tensor, target: torch.Tensor, jaccard: bool = False,
     return f.mean()
 
 
+def dice_ce_loss(logits: torch.Tensor, target: torch.Tensor, lambda_dice: float = 1.0, lambda_ce: float = 1.0,
+                 jaccard: bool = False) -> torch.Tensor:
+    """learning/losses.py:470-595 (DiceCELoss as built at src/definer.py:204-212): the Dice term above plus
+    CrossEntropyLoss(input, argmax(target, dim=1)) with mean reduction (`ce()`, losses.py:562-577)."""
+    y = torch.argmax(target.float(), dim=1).long()
+    ce = torch.nn.functional.cross_entropy(logits.float(), y, reduction="mean")
+    return lambda_dice * dice_loss(logits, target, jaccard) + lambda_ce * ce
+
+
 def deep_supervision_loss(heads: Sequence[torch.Tensor], target: torch.Tensor, jaccard: bool = False):
     """mean_k criterion(head_k, target) over main output + deep heads (engine.py:322-330)."""
     return torch.stack([dice_loss(h, target, jaccard) for h in heads]).mean()

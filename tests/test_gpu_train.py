@@ -281,6 +281,37 @@ def test_ranger_step_matches_oracle():
             assert torch.allclose(p.detach(), r, rtol=2e-5, atol=2e-6), f"step {step + 1}"
 
 
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("weighted", {"lambda_dice": 0.7, "lambda_ce": 1.3})])
+def test_dice_ce_loss_matches_reference_golden_and_oracle(golden_dir, tag, kw):
+    """DiceCELoss (--criterion dice_ce): fused kernels vs the golden produced by the unmodified
+    learning.losses.DiceCELoss, and vs the oracle at a larger odd size."""
+    import os
+    import numpy as np
+    from brats21_b200.losses import DiceCELoss
+    from oracle import train as otrain
+    from test_oracle_golden import _dice_ce_inputs
+    g = np.load(os.path.join(golden_dir, "dice_ce.npz"))
+    x, t = _dice_ce_inputs()
+    crit = DiceCELoss(include_background=True, sigmoid=True, softmax=False, squared_pred=True, batch=True,
+                      reduction="mean", **kw)
+    xg = x.to(DEV).requires_grad_(True)
+    loss = crit(xg, t.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{tag}_loss"])) <= 2e-5
+    assert _rel(xg.grad.cpu(), torch.from_numpy(g[f"{tag}_grad"])) <= 1e-4
+    gen = torch.Generator(device=DEV).manual_seed(31)
+    x2 = (torch.randn((1, 3, 21, 17, 13), device=DEV, generator=gen) * 3).requires_grad_(True)
+    t2 = (torch.rand((1, 3, 21, 17, 13), device=DEV, generator=gen) > 0.6).float()
+    l2 = crit(x2, t2)
+    (l2 * 0.5).backward()
+    xr = x2.detach().clone().requires_grad_(True)
+    lr = otrain.dice_ce_loss(xr, t2, **kw)
+    (lr * 0.5).backward()
+    assert abs(l2.item() - lr.item()) <= 2e-5 and _rel(x2.grad, xr.grad) <= 1e-4
+    with pytest.raises(ValueError):
+        DiceCELoss(sigmoid=True, squared_pred=True, batch=True, lambda_ce=-1.0)
+
+
 def _v2_reference_grads(params, x, target, jaccard=False):
     from oracle import nets
     from oracle import train as otrain

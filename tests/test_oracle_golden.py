@@ -131,3 +131,24 @@ def test_label_postprocessing():
     y, pb, pa = oinf.shape_to_divisible(x, 8)
     assert y.shape[-3:] == (240, 240, 160) and pb.tolist() == [0, 0, 3] and pa.tolist() == [0, 0, 2]
     assert oinf.shape_to_original(y, pb, pa).shape == x.shape
+
+
+def _dice_ce_inputs():
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn((2, 3, 6, 5, 7), generator=g) * 2.0
+    wt = torch.rand((2, 1, 6, 5, 7), generator=g) > 0.5
+    tc = wt & (torch.rand((2, 1, 6, 5, 7), generator=g) > 0.4)
+    et = tc & (torch.rand((2, 1, 6, 5, 7), generator=g) > 0.5)
+    return x, torch.cat([tc, wt, et], dim=1).float()
+
+
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("weighted", {"lambda_dice": 0.7, "lambda_ce": 1.3})])
+def test_dice_ce_loss_matches_reference(golden_dir, tag, kw):
+    """oracle.train.dice_ce_loss against the unmodified learning.losses.DiceCELoss (tests/golden/make_golden_losses.py)."""
+    g = _load(golden_dir, "dice_ce.npz")
+    x, t = _dice_ce_inputs()
+    xr = x.clone().requires_grad_(True)
+    loss = train.dice_ce_loss(xr, t, **kw)
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{tag}_loss"])) <= 1e-6
+    assert np.abs(xr.grad.numpy() - g[f"{tag}_grad"]).max() <= 1e-7
