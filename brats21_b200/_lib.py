@@ -33,6 +33,9 @@ _SIGNATURES = {
     "b21_conv_point_supported": [_i, _i],
     "b21_conv1x1_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _vp],
     "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _vp],
+    "b21_channel_stats": [_vp, _i, _vp, _i, _i64, _i, _vp],
+    "b21_norm_coeffs": [_i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i64, _f, _vp],
+    "b21_affine_act": [_vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i64, _i, _vp],
     "b21_se_gate": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "b21_scale_pool": [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_upsample2x": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -30,19 +30,29 @@ def _conv1(cin, cout, bias=True):
     return nn.Conv3d(cin, cout, kernel_size=1, bias=bias)
 
 
-class ConvBnRelu(nn.Sequential):
-    """Parameter holder mirroring equiunet2020.py:51-75 (conv -> GroupNorm(8) -> act -> dropout)."""
+_NORMS = {"group": lambda c: nn.GroupNorm(8, c, affine=True), "instance": lambda c: nn.InstanceNorm3d(c, affine=True),
+          "batch": lambda c: nn.BatchNorm3d(c, affine=True), "none": None}   # get_norm_layer, factory.py:179-192
+_ACTS = {"relu": lambda: nn.ReLU(inplace=True), "leakyrelu": lambda: nn.LeakyReLU(inplace=True),
+         "elu": lambda: nn.ELU(inplace=True)}                                 # get_act, factory.py:195-200 (MONAI Act)
 
-    def __init__(self, cin, cout, act, dil=1, dropout=0.0):
-        super().__init__(OrderedDict([("conv", _conv3(cin, cout, dil)), ("bn", nn.GroupNorm(8, cout, affine=True)),
-                                      (act, nn.ReLU(inplace=True)), ("dropout", nn.Dropout(p=dropout))]))
+
+class ConvBnRelu(nn.Sequential):
+    """Parameter holder mirroring equiunet2020.py:51-75: conv (bias only without a norm) -> norm -> act -> dropout,
+    with the reference's sub-module names (the activation is registered under its own name)."""
+
+    def __init__(self, cin, cout, act, dil=1, dropout=0.0, norm="group"):
+        mods = [("conv", _conv3(cin, cout, dil, bias=_NORMS[norm] is None))]
+        if _NORMS[norm] is not None:
+            mods.append(("bn", _NORMS[norm](cout)))
+        mods += [(act, _ACTS[act]()), ("dropout", nn.Dropout(p=dropout))]
+        super().__init__(OrderedDict(mods))
         self.dil = dil
 
 
 class UBlock(nn.Sequential):
-    def __init__(self, cin, mid, cout, act, dils=(1, 1), dropout=0.0):
-        super().__init__(OrderedDict([("ConvBnRelu1", ConvBnRelu(cin, mid, act, dils[0], dropout)),
-                                      ("ConvBnRelu2", ConvBnRelu(mid, cout, act, dils[1], dropout))]))
+    def __init__(self, cin, mid, cout, act, dils=(1, 1), dropout=0.0, norm="group"):
+        super().__init__(OrderedDict([("ConvBnRelu1", ConvBnRelu(cin, mid, act, dils[0], dropout, norm)),
+                                      ("ConvBnRelu2", ConvBnRelu(mid, cout, act, dils[1], dropout, norm))]))
 
 
 class EvoNorm3D(nn.Module):
@@ -245,10 +255,12 @@ class EquiUnet(_B21Net):
     def __init__(self, inplanes, num_classes, features, norm_layer=None, act="relu", deep_supervision=False,
                  dropout=0, refinement=False):
         super().__init__()
-        if norm_layer not in ("group",):
-            raise NotImplementedError("only norm_layer='group' (GroupNorm(8)) is on the accelerated path")
-        if act != "relu":
-            raise NotImplementedError("only act='relu' is on the accelerated V1 path")
+        if norm_layer == "bcn":
+            raise NotImplementedError("norm_layer='bcn' (BCNorm, factory.py:128-176) is not on the accelerated path")
+        if norm_layer not in _NORMS:
+            raise ValueError("Norm type is not correct")  # get_norm_layer, factory.py:192
+        if act not in _ACTS:
+            raise NotImplementedError(f"act={act!r}: only relu / leakyrelu / elu are on the accelerated path")
         if refinement:
             raise NotImplementedError("refinement (RefUnet) is out of scope (SURVEY.md §0)")
         if dropout:
@@ -256,16 +268,18 @@ class EquiUnet(_B21Net):
         f = list(features)
         self.inplanes, self.num_classes, self.features = inplanes, num_classes, f
         self.deep_supervision, self.act, self.refinement = deep_supervision, act, refinement
-        self.encoder1 = UBlock(inplanes, f[0], f[0], act)
-        self.encoder2 = UBlock(f[0], f[1], f[1], act)
-        self.encoder3 = UBlock(f[1], f[2], f[2], act)
-        self.encoder4 = UBlock(f[2], f[3], f[3], act)
-        self.bottom = UBlock(f[3], f[3], f[3], act, (2, 2))
-        self.bottom_2 = ConvBnRelu(f[3] * 2, f[2], act)
+        self.norm = norm_layer
+        kw = dict(norm=norm_layer)
+        self.encoder1 = UBlock(inplanes, f[0], f[0], act, **kw)
+        self.encoder2 = UBlock(f[0], f[1], f[1], act, **kw)
+        self.encoder3 = UBlock(f[1], f[2], f[2], act, **kw)
+        self.encoder4 = UBlock(f[2], f[3], f[3], act, **kw)
+        self.bottom = UBlock(f[3], f[3], f[3], act, (2, 2), **kw)
+        self.bottom_2 = ConvBnRelu(f[3] * 2, f[2], act, **kw)
         self.downsample = nn.MaxPool3d(2, 2)
-        self.decoder3 = UBlock(f[2] * 2, f[2], f[1], act)
-        self.decoder2 = UBlock(f[1] * 2, f[1], f[0], act)
-        self.decoder1 = UBlock(f[0] * 2, f[0], f[0], act)
+        self.decoder3 = UBlock(f[2] * 2, f[2], f[1], act, **kw)
+        self.decoder2 = UBlock(f[1] * 2, f[1], f[0], act, **kw)
+        self.decoder1 = UBlock(f[0] * 2, f[0], f[0], act, **kw)
         self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
         self.outconv = _conv1(f[0], num_classes)
         if deep_supervision:
@@ -273,10 +287,14 @@ class EquiUnet(_B21Net):
             self.deep_bottom2 = _head(f[2], num_classes, 8)
             self.deep3 = _head(f[1], num_classes, 4)
             self.deep2 = _head(f[0], num_classes, 2)
-        # init_weights(self, "kaiming") (factory.py:203-224): kaiming-normal fan_out on every Conv weight
+        # init_weights(self, "kaiming") (factory.py:203-224): kaiming-normal fan_out on every Conv weight (biases keep
+        # torch's default), N(1, 0.02) / 0 on BatchNorm weight / bias — drawn in module order, as net.apply() does
         for m in self.modules():
             if isinstance(m, nn.Conv3d):
                 nn.init.kaiming_normal_(m.weight.data, a=0.0, mode="fan_out")
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.normal_(m.weight.data, 1.0, 0.02)
+                nn.init.constant_(m.bias.data, 0.0)
         self._init_runtime()
 
     _CBR = ["encoder1.ConvBnRelu1", "encoder1.ConvBnRelu2", "encoder2.ConvBnRelu1", "encoder2.ConvBnRelu2",
@@ -288,19 +306,28 @@ class EquiUnet(_B21Net):
         for name in self._CBR:
             m = self.get_submodule(name)
             self._pc(name, m.conv, cin_padded=8 if name == "encoder1.ConvBnRelu1" else None)
-            self._vec(name + ".g", m.bn.weight)
-            self._vec(name + ".b", m.bn.bias)
+            if self.norm != "none":
+                self._vec(name + ".g", m.bn.weight)
+                self._vec(name + ".b", m.bn.bias)
         heads = ["outconv"] + (["deep_bottom.0", "deep_bottom2.0", "deep3.0", "deep2.0"] if self.deep_supervision else [])
         for name in heads:
             m = self.get_submodule(name)
             self._mat(name + ".w", m.weight)
             self._vec(name + ".bias", m.bias)
 
+    def _recipe(self) -> bool:
+        """GroupNorm(8) + ReLU — the README recipe — has the dedicated fused normalisation kernel and the training path."""
+        return self.norm == "group" and self.act == "relu"
+
     def _grad_order(self):
         from .autograd import v1_grad_order
         return v1_grad_order(self)
 
     def _forward_train(self, x8, want_deep):
+        if not self._recipe():
+            raise NotImplementedError(f"EquiUnet(norm_layer={self.norm!r}, act={self.act!r}): the accelerated BACKWARD "
+                                      "covers GroupNorm(8) + ReLU (the reference recipes, README.md:103-121); other "
+                                      "factory combinations run forward / inference only")
         from .autograd import _v1_forward_train
         return _v1_forward_train(self, x8, want_deep)
 
@@ -310,9 +337,27 @@ class EquiUnet(_B21Net):
 
     def _cbr(self, name, x, out, stats, dil=1):
         p = self._packed
-        ops.conv3d(x, p[name], out=out, stats=stats, dil=dil)
-        ops.norm_apply(out, stats, p[name + ".g"], p[name + ".b"], ops.GN_RELU)
-        return out
+        if self._recipe():
+            ops.conv3d(x, p[name], out=out, stats=stats, dil=dil)
+            ops.norm_apply(out, stats, p[name + ".g"], p[name + ".b"], ops.GN_RELU)
+            return out
+        # the rest of the factory (networks/factory.py:179-200): statistics -> per-(n, c) affine -> activation
+        if self.norm == "none":
+            ops.conv3d(x, p[name], out=out, dil=dil)  # the conv carries the bias (equiunet2020.py:68)
+            return ops.norm_act(out, ops.NORM_NONE, self.act)
+        if self.norm == "group":
+            ops.conv3d(x, p[name], out=out, stats=stats, dil=dil)
+            return ops.norm_act(out, ops.NORM_GROUP, self.act, p[name + ".g"], p[name + ".b"], conv_stats=stats)
+        ops.conv3d(x, p[name], out=out, dil=dil)
+        if self.norm == "instance":
+            return ops.norm_act(out, ops.NORM_INSTANCE, self.act, p[name + ".g"], p[name + ".b"])
+        bn = self.get_submodule(name).bn
+        if self.training:  # batch statistics; running statistics updated in place, as nn.BatchNorm3d.forward does
+            bn.num_batches_tracked += 1
+            return ops.norm_act(out, ops.NORM_BATCH_TRAIN, self.act, p[name + ".g"], p[name + ".b"],
+                                running=(bn.running_mean, bn.running_var), momentum=bn.momentum)
+        return ops.norm_act(out, ops.NORM_BATCH_EVAL, self.act, p[name + ".g"], p[name + ".b"],
+                            running=(bn.running_mean, bn.running_var))
 
     def forward_packed(self, x8: torch.Tensor, want_deep: bool = True):
         """x8: [N, D, H, W, 8] bf16 channels-last (modalities in channels 0..3). Returns (logits, [deep heads])."""

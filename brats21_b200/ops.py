@@ -295,6 +295,34 @@ def norm_apply(x, stats, gamma, beta, mode, out=None, chan_sum=None, eps=1e-5):
     return out
 
 
+NORM_GROUP, NORM_INSTANCE, NORM_BATCH_TRAIN, NORM_BATCH_EVAL, NORM_NONE = 0, 1, 2, 3, 4
+ACT_CODES = {"none": 0, "relu": 1, "leakyrelu": 2, "elu": 3}
+
+
+def norm_act(x, kind, act, gamma=None, beta=None, conv_stats=None, running=None, momentum=0.1, out=None, slope=0.01,
+             eps=1e-5):
+    """The general norm + activation of EquiUnet's factory (networks/factory.py:179-200) after a conv: statistics
+    (per channel for instance / batch norm, the conv epilogue's group statistics for GroupNorm) -> per-(n, c) affine ->
+    y = act(a * x + b).  running = (running_mean, running_var) for batch norm.  In place when out is None."""
+    n, d, h, w, c = x.shape
+    nvox = d * h * w
+    if out is None:
+        out = x
+    stats = conv_stats
+    if kind in (NORM_INSTANCE, NORM_BATCH_TRAIN):
+        stats = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+        with _hbm("channel_stats", 2.0 * n * nvox * c):
+            call("b21_channel_stats", ptr(x), _ld(x), ptr(stats), n, nvox, c, stream_ptr())
+    ab = torch.empty((2, n, c), dtype=torch.float32, device=x.device)
+    rm, rv = running if running is not None else (None, None)
+    call("b21_norm_coeffs", kind, ptr(stats), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(momentum), ptr(ab[0]),
+         ptr(ab[1]), n, c, nvox, eps, stream_ptr())
+    with _hbm("affine_act", 4.0 * n * nvox * c):
+        call("b21_affine_act", ptr(x), _ld(x), ptr(out), _ld(out), ptr(ab[0]), ptr(ab[1]), ACT_CODES[act], float(slope),
+             n, nvox, c, stream_ptr())
+    return out
+
+
 def se_gate(chan_sum, w1, b1, w2, b2, nvox):
     n, c = chan_sum.shape
     scale = torch.empty_like(chan_sum)

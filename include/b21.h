@@ -142,6 +142,21 @@ int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const double* stats
                    const float* beta, float* chan_sum, int mode, int n, long long nvox, int c, float eps,
                    void* stream);
 
+/* The rest of the norm / activation factory of EquiUnet (networks/factory.py:179-200: get_norm_layer "instance" =
+ * nn.InstanceNorm3d(affine), "batch" = nn.BatchNorm3d(affine), "none"; get_act "relu" | "leakyrelu" | "elu" through
+ * MONAI's Act), as three passes: b21_channel_stats (per (n, c) sum / sum of squares over the voxels, double
+ * out[n][c][2]), b21_norm_coeffs (statistics -> per-(n, c) affine a, b with y = a*x + b the normalisation; kind 0 =
+ * GroupNorm(8) from the conv-epilogue statistics, 1 = instance, 2 = batch norm in training mode (batch statistics over
+ * n and voxels; running_mean / running_var updated with `momentum`, unbiased variance, as nn.BatchNorm3d), 3 = batch
+ * norm in eval mode (running statistics), 4 = none (a = 1, b = 0)), and b21_affine_act (y = act(a[n][c]*x + b[n][c]),
+ * act 0 identity / 1 ReLU / 2 LeakyReLU(slope) / 3 ELU(alpha = 1); x may alias y). */
+int b21_channel_stats(const void* x, int ldx, double* out, int n, long long nvox, int c, void* stream);
+int b21_norm_coeffs(int kind, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float* a_out, float* b_out, int n, int c, long long nvox,
+                    float eps, void* stream);
+int b21_affine_act(const void* x, int ldx, void* y, int ldy, const float* a, const float* b, int act, float slope, int n,
+                   long long nvox, int c, void* stream);
+
 /* MONAI ResidualSELayer(r=2, relu, sigmoid) gate used at networks/equiunet2021.py:204-205:
  * scale[n][c] = 1 + sigmoid(W2 relu(W1 (chan_sum[n] * inv_count) + b1) + b2), so that x + x*s == x*scale. */
 int b21_se_gate(const float* chan_sum, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -63,14 +63,39 @@ def up_trilinear(x: torch.Tensor, scale: int = 2) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ V1
-def _v1_cbr(p: Params, key: str, x: torch.Tensor, dil: int = 1) -> torch.Tensor:
+def activation(y: torch.Tensor, act: str) -> torch.Tensor:
+    """get_act (factory.py:195-200) through MONAI's Act table: relu | leakyrelu (slope 0.01) | elu (alpha 1)."""
+    if act == "relu":
+        return torch.relu(y)
+    if act == "leakyrelu":
+        return F.leaky_relu(y, 0.01)
+    if act == "elu":
+        return F.elu(y)
+    raise KeyError(act)
+
+
+def _v1_cbr(p: Params, key: str, x: torch.Tensor, dil: int = 1, norm: str = "group", act: str = "relu",
+            training: bool = False) -> torch.Tensor:
+    """ConvBnRelu (equiunet2020.py:51-75) for every norm of get_norm_layer (factory.py:179-192) except "bcn"."""
+    if norm == "none":
+        return activation(F.conv3d(x, p[f"{key}.conv.weight"], p[f"{key}.conv.bias"], padding=dil, dilation=dil), act)
     y = F.conv3d(x, p[f"{key}.conv.weight"], None, padding=dil, dilation=dil)
-    return group_norm_relu(y, p[f"{key}.bn.weight"], p[f"{key}.bn.bias"])
+    g, b = p[f"{key}.bn.weight"], p[f"{key}.bn.bias"]
+    if norm == "group":
+        if act == "relu":
+            return group_norm_relu(y, g, b)
+        return activation(F.group_norm(y, 8, g, b, 1e-5), act)
+    if norm == "instance":  # nn.InstanceNorm3d(affine=True): per (n, c) statistics, biased variance, eps 1e-5
+        return activation(F.instance_norm(y, None, None, g, b, True, 0.1, 1e-5), act)
+    if norm == "batch":     # nn.BatchNorm3d(affine=True); training updates the running statistics in place
+        rm, rv = p[f"{key}.bn.running_mean"], p[f"{key}.bn.running_var"]
+        return activation(F.batch_norm(y, rm, rv, g, b, training, 0.1, 1e-5), act)
+    raise ValueError("Norm type is not correct")
 
 
-def _v1_ublock(p: Params, key: str, x: torch.Tensor, dils=(1, 1)) -> torch.Tensor:
-    x = _v1_cbr(p, f"{key}.ConvBnRelu1", x, dils[0])
-    return _v1_cbr(p, f"{key}.ConvBnRelu2", x, dils[1])
+def _v1_ublock(p: Params, key: str, x: torch.Tensor, dils=(1, 1), **kw) -> torch.Tensor:
+    x = _v1_cbr(p, f"{key}.ConvBnRelu1", x, dils[0], **kw)
+    return _v1_cbr(p, f"{key}.ConvBnRelu2", x, dils[1], **kw)
 
 
 def _head(p: Params, key: str, x: torch.Tensor, scale: int) -> torch.Tensor:
@@ -78,17 +103,19 @@ def _head(p: Params, key: str, x: torch.Tensor, scale: int) -> torch.Tensor:
     return up_trilinear(y, scale) if scale > 1 else y
 
 
-def equiunet_v1_forward(p: Params, x: torch.Tensor, deep_supervision: bool = True):
+def equiunet_v1_forward(p: Params, x: torch.Tensor, deep_supervision: bool = True, norm: str = "group",
+                        act: str = "relu", training: bool = False):
     """equiunet2020.py:467-500."""
-    down1 = _v1_ublock(p, "encoder1", x)
-    down2 = _v1_ublock(p, "encoder2", F.max_pool3d(down1, 2))
-    down3 = _v1_ublock(p, "encoder3", F.max_pool3d(down2, 2))
-    down4 = _v1_ublock(p, "encoder4", F.max_pool3d(down3, 2))
-    bottom = _v1_ublock(p, "bottom", down4, (2, 2))
-    bottom_2 = _v1_cbr(p, "bottom_2", torch.cat([down4, bottom], dim=1))
-    up3 = _v1_ublock(p, "decoder3", torch.cat([down3, up_trilinear(bottom_2)], dim=1))
-    up2 = _v1_ublock(p, "decoder2", torch.cat([down2, up_trilinear(up3)], dim=1))
-    up1 = _v1_ublock(p, "decoder1", torch.cat([down1, up_trilinear(up2)], dim=1))
+    kw = dict(norm=norm, act=act, training=training)
+    down1 = _v1_ublock(p, "encoder1", x, **kw)
+    down2 = _v1_ublock(p, "encoder2", F.max_pool3d(down1, 2), **kw)
+    down3 = _v1_ublock(p, "encoder3", F.max_pool3d(down2, 2), **kw)
+    down4 = _v1_ublock(p, "encoder4", F.max_pool3d(down3, 2), **kw)
+    bottom = _v1_ublock(p, "bottom", down4, (2, 2), **kw)
+    bottom_2 = _v1_cbr(p, "bottom_2", torch.cat([down4, bottom], dim=1), **kw)
+    up3 = _v1_ublock(p, "decoder3", torch.cat([down3, up_trilinear(bottom_2)], dim=1), **kw)
+    up2 = _v1_ublock(p, "decoder2", torch.cat([down2, up_trilinear(up3)], dim=1), **kw)
+    up1 = _v1_ublock(p, "decoder1", torch.cat([down1, up_trilinear(up2)], dim=1), **kw)
     out = _head(p, "outconv", up1, 1)
     if not deep_supervision:
         return out
@@ -142,15 +169,24 @@ def equiunet_v2_forward(p: Params, x: torch.Tensor, deep_supervision: bool = Tru
 
 
 # ------------------------------------------------------------------------------------------ parameter specs
-def v1_param_shapes(width: int = 48, inplanes: int = 4, num_classes: int = 3) -> List[Tuple[str, Tuple[int, ...]]]:
-    """state_dict entries of the reference EquiUnet in registration order."""
+def v1_param_shapes(width: int = 48, inplanes: int = 4, num_classes: int = 3,
+                    norm: str = "group") -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict entries of the reference EquiUnet in registration order; `norm` as
+    get_norm_layer (factory.py:179-192): "none" gives the convs a bias and no `bn`, "batch" adds the BatchNorm buffers."""
     f = [width * 2 ** i for i in range(4)]
     out: List[Tuple[str, Tuple[int, ...]]] = []
 
     def cbr(key, cin, cout):
         out.append((f"{key}.conv.weight", (cout, cin, 3, 3, 3)))
+        if norm == "none":
+            out.append((f"{key}.conv.bias", (cout,)))
+            return
         out.append((f"{key}.bn.weight", (cout,)))
         out.append((f"{key}.bn.bias", (cout,)))
+        if norm == "batch":
+            out.append((f"{key}.bn.running_mean", (cout,)))
+            out.append((f"{key}.bn.running_var", (cout,)))
+            out.append((f"{key}.bn.num_batches_tracked", ()))
 
     def ublock(key, cin, mid, cout):
         cbr(f"{key}.ConvBnRelu1", cin, mid)

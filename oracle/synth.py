@@ -15,11 +15,11 @@ from brats21_b200.synth import _gen, ellipsoid_mask, target, volume  # noqa: F40
 
 
 def make_params(version: int, width: int = 48, seed: int = 123, perturb_affine: bool = True,
-                inplanes: int = 4, num_classes: int = 3) -> Dict[str, torch.Tensor]:
+                inplanes: int = 4, num_classes: int = 3, norm: str = "group") -> Dict[str, torch.Tensor]:
     """Reference-format state_dict with the reference's init DISTRIBUTIONS (V1: kaiming-normal fan_out on convs,
     networks/factory.py:209-210; V2: torch defaults, equiunet2021.py:287) drawn from name-keyed generators.
     With perturb_affine the norm scales/offsets are jittered so that parity tests exercise them."""
-    spec = nets.v1_param_shapes(width, inplanes, num_classes) if version == 1 else \
+    spec = nets.v1_param_shapes(width, inplanes, num_classes, norm) if version == 1 else \
         nets.v2_param_shapes(width, inplanes, num_classes)
     out: Dict[str, torch.Tensor] = {}
     for name, shape in spec:
@@ -46,9 +46,15 @@ def make_params(version: int, width: int = 48, seed: int = 123, perturb_affine: 
             t = torch.zeros(shape)
             if perturb_affine:
                 t = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "running_mean":  # BatchNorm buffers: non-trivial values so that eval mode exercises them
+            t = 0.2 * torch.randn(shape, generator=g)
+        elif leaf == "running_var" and ".bn." in name:
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif leaf == "num_batches_tracked":
+            t = torch.zeros(shape, dtype=torch.long)
         elif leaf in ("v", "running_var"):
             t = torch.ones(shape)
         else:
             raise KeyError(name)
-        out[name] = t.float()
+        out[name] = t if t.dtype == torch.long else t.float()
     return out

@@ -20,6 +20,7 @@ from oracle import ref_loader, synth  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 WIDTH = 16
 SHAPE = (32, 32, 32)
+VARIANTS = (("instance", "leakyrelu"), ("batch", "elu"), ("none", "relu"), ("group", "leakyrelu"), ("instance", "relu"))
 
 
 def ramp_predictor(x: torch.Tensor) -> torch.Tensor:
@@ -56,6 +57,29 @@ def main():
         rec["keys"] = np.array(sorted(net.state_dict().keys()))
         np.savez_compressed(os.path.join(HERE, f"net_v{ver}_w{WIDTH}.npz"), **rec)
         print(f"v{ver}: out {tuple(out.shape)} mean {out.mean():.5f} std {out.std():.5f}", missing)
+
+    # ---- the rest of the norm / act factory (networks/factory.py:179-200) on EquiUnet: 16^3 inputs
+    rec = {}
+    xv = synth.volume(seed=3, shape=(16, 16, 16))
+    for norm, act in VARIANTS:
+        with ref_loader.quiet():
+            net = ref.equiunet2020.EquiUnet(4, 3, feats, norm_layer=norm, act=act, deep_supervision=True)
+        net.load_state_dict(synth.make_params(1, WIDTH, 123, norm=norm), strict=True)
+        net.eval()
+        with torch.no_grad():
+            out, deeps = net(xv)
+        tag = f"{norm}_{act}"
+        rec[f"{tag}_out"] = out.numpy()
+        rec[f"{tag}_deep0_s2"] = deeps[0][..., ::2, ::2, ::2].contiguous().numpy()
+        rec[f"{tag}_keys"] = np.array(list(net.state_dict().keys()))
+        if norm == "batch":  # training-mode forward: batch statistics, running statistics updated
+            net.train()
+            with torch.no_grad():
+                out, _ = net(xv)
+            rec[f"{tag}_train_out"] = out.numpy()
+            rec[f"{tag}_train_running_mean"] = net.encoder1.ConvBnRelu1.bn.running_mean.numpy().copy()
+            rec[f"{tag}_train_running_var"] = net.decoder1.ConvBnRelu2.bn.running_var.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "net_v1_w16_variants.npz"), **rec)
 
     # ---- sliding window (reference utils/inferers.py), odd sizes, both blend modes, image smaller than roi
     sw = {}

@@ -169,3 +169,46 @@ def test_v2_level3_fold_matches_explicit_level3(width, shape, n):
         _check(a, b)
     assert ((out_f - out_e).norm() / out_e.norm()).item() <= 1.5e-2
     assert ((deeps_f[0] - deeps_e[0]).norm() / deeps_e[0].norm()).item() <= 1.5e-2
+
+
+@pytest.mark.parametrize("norm,act", [("instance", "leakyrelu"), ("batch", "elu"), ("none", "relu"), ("group", "leakyrelu"),
+                                      ("instance", "relu")])
+def test_v1_norm_act_factory(golden_dir, norm, act):
+    """EquiUnet under the rest of networks/factory.py:179-200 (get_norm_layer instance / batch / none, get_act leakyrelu
+    / elu): channel_stats -> norm_coeffs -> affine_act, vs the unmodified-reference golden and the oracle; batch norm in
+    eval mode (running statistics) and in training-mode forward (batch statistics, running statistics updated)."""
+    import warnings
+    from brats21_b200 import networks
+    from oracle import nets, synth
+    g = np.load(os.path.join(golden_dir, "net_v1_w16_variants.npz"))
+    tag = f"{norm}_{act}"
+    params = {k: v.to(DEV) for k, v in synth.make_params(1, 16, 123, norm=norm).items()}
+    net = networks.EquiUnet(4, 3, [16, 32, 64, 128], norm_layer=norm, act=act, deep_supervision=True).to(DEV).eval()
+    assert list(net.state_dict().keys()) == list(g[f"{tag}_keys"])
+    net.load_state_dict(params, strict=True)
+    x = synth.volume(seed=3, shape=(16, 16, 16)).to(DEV)
+    out, deeps = net(x)
+    _check(out.cpu(), torch.from_numpy(g[f"{tag}_out"]))
+    _check(deeps[0][..., ::2, ::2, ::2].cpu(), torch.from_numpy(g[f"{tag}_deep0_s2"]))
+    # a larger, batched, non-cubic input against the oracle
+    xb = torch.cat([synth.volume(seed=s, shape=(16, 24, 40)) for s in range(2)]).to(DEV)
+    with torch.no_grad():
+        ref, _ = nets.equiunet_v1_forward(params, xb, norm=norm, act=act)
+    _check(net(xb)[0], ref)
+    if norm == "batch":
+        net.train()
+        with torch.no_grad():
+            out_t, _ = net(x)
+        _check(out_t.cpu(), torch.from_numpy(g[f"{tag}_train_out"]))
+        sd = net.state_dict()
+        assert (sd["encoder1.ConvBnRelu1.bn.running_mean"].cpu() -
+                torch.from_numpy(g[f"{tag}_train_running_mean"])).abs().max().item() <= 2e-3
+        assert (sd["decoder1.ConvBnRelu2.bn.running_var"].cpu() -
+                torch.from_numpy(g[f"{tag}_train_running_var"])).abs().max().item() <= 2e-2
+        assert int(sd["encoder1.ConvBnRelu1.bn.num_batches_tracked"]) == 1
+    if (norm, act) != ("group", "relu"):
+        net.train()
+        with pytest.raises(NotImplementedError):
+            net(x.requires_grad_(True))
+    with pytest.raises(ValueError):
+        networks.EquiUnet(4, 3, [16, 32, 64, 128], norm_layer=None)

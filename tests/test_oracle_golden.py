@@ -152,3 +152,29 @@ def test_dice_ce_loss_matches_reference(golden_dir, tag, kw):
     loss.backward()
     assert abs(loss.item() - float(g[f"{tag}_loss"])) <= 1e-6
     assert np.abs(xr.grad.numpy() - g[f"{tag}_grad"]).max() <= 1e-7
+
+
+V1_VARIANTS = (("instance", "leakyrelu"), ("batch", "elu"), ("none", "relu"), ("group", "leakyrelu"), ("instance", "relu"))
+
+
+@pytest.mark.parametrize("norm,act", V1_VARIANTS)
+def test_v1_norm_act_factory_matches_reference(golden_dir, norm, act):
+    """EquiUnet under the other norms / activations of networks/factory.py:179-200 (unmodified reference golden)."""
+    g = _load(golden_dir, "net_v1_w16_variants.npz")
+    tag = f"{norm}_{act}"
+    x = synth.volume(seed=3, shape=(16, 16, 16))
+    p = synth.make_params(1, WIDTH, 123, norm=norm)
+    assert list(p.keys()) == list(g[f"{tag}_keys"])  # state_dict key ORDER too
+    with torch.no_grad():
+        out, deeps = nets.equiunet_v1_forward(p, x, norm=norm, act=act)
+    ref = torch.from_numpy(g[f"{tag}_out"])
+    assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    r0 = torch.from_numpy(g[f"{tag}_deep0_s2"])
+    assert (deeps[0][..., ::2, ::2, ::2] - r0).abs().max().item() <= 2e-4 * max(r0.abs().max().item(), 1.0)
+    if norm == "batch":
+        with torch.no_grad():
+            out, _ = nets.equiunet_v1_forward(p, x, norm=norm, act=act, training=True)
+        ref = torch.from_numpy(g[f"{tag}_train_out"])
+        assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+        assert np.abs(p["encoder1.ConvBnRelu1.bn.running_mean"].numpy() - g[f"{tag}_train_running_mean"]).max() <= 1e-5
+        assert np.abs(p["decoder1.ConvBnRelu2.bn.running_var"].numpy() - g[f"{tag}_train_running_var"]).max() <= 1e-5
