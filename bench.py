@@ -338,12 +338,36 @@ def measure_train(args, dx: Dist, steps: int, warmup: int, seed: int = 93):
     def step_device():
         return graphed(img_dev, tgt_dev)
 
+    # e2e: every step copies ITS batch from pinned host memory and reads its loss back; as a DataLoader with
+    # pin_memory + non_blocking does, the copy of the next batch runs on a copy stream under the current step
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = [[torch.empty_like(img_dev), torch.empty_like(tgt_dev), None] for _ in range(2)]
+    state = {"i": 0}
+
+    def stage(slot):
+        with torch.cuda.stream(copy_stream):
+            if slot[2] is not None:
+                copy_stream.wait_event(slot[2])  # the step that last read this slot has finished with it
+            slot[0].copy_(host_img, non_blocking=True)
+            slot[1].copy_(host_tgt, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    ready = [stage(staged[0]), None]
+
     def step_e2e():
-        img = host_img.to(dev, non_blocking=True)
-        tgt = host_tgt.to(dev, non_blocking=True)
-        loss = graphed(img, tgt)
+        i = state["i"]
+        cur, nxt = staged[i % 2], staged[(i + 1) % 2]
+        ready[(i + 1) % 2] = stage(nxt)                      # prefetch the next batch
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        loss = graphed(cur[0], cur[1])
+        done = torch.cuda.Event()
+        done.record()
+        cur[2] = done
         host_loss.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        state["i"] = i + 1
 
     for _ in range(max(warmup, graphed.eager_warmup + 1)):
         step_device()
@@ -633,9 +657,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the `train` block of the default workload")
     ap.add_argument("--cohort", type=int, default=219, help="volumes of the v2_ens3_tta8_cohort workload")
+    ap.add_argument("--sw-batch", type=int, default=0, help="override the workload's sliding-window batch size")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.sw_batch > 0 and "sw_batch" in wl:
+        wl["sw_batch"] = args.sw_batch
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:
