@@ -117,8 +117,7 @@ def count_map(image_size, roi, overlap, mode, sigma_scale, device) -> torch.Tens
         prof = importance_profiles(roi, mode, sigma_scale, device)
         origins = window_origins(image_size, roi, overlap)
         floor = importance_floor(prof)
-        for i in range(0, len(origins), 16):
-            ops.blend_accumulate(None, cnt, prof, origins[i:i + 16], floor)
+        ops.blend_accumulate(None, cnt, prof, origins, floor)
         _count_cache[key] = cnt
         while len(_count_cache) > _COUNT_CACHE_ENTRIES:
             _count_cache.popitem(last=False)

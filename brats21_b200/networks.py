@@ -207,9 +207,7 @@ class _B21Net(nn.Module):
         x = x.detach().to(torch.float32).contiguous()
         ws = self._ws.setdefault(("in", n, d, h, w), {})
         out = self._buf(ws, "x8", (n, d, h, w, 8))
-        for b0 in range(0, n, 16):
-            nb = min(16, n - b0)
-            ops.pack_windows(x, out[b0:b0 + nb], [(0, 0, 0)] * nb, vol_index=list(range(b0, b0 + nb)))
+        ops.pack_windows(x, out, [(0, 0, 0)] * n, vol_index=list(range(n)))
         return out
 
     def forward_infer(self, x8: torch.Tensor) -> torch.Tensor:

@@ -380,15 +380,21 @@ def _iarr(vals):
     return (_C.c_int * len(vals))(*vals)
 
 
+MAX_WINDOWS_PER_CALL = 16  # kMaxWin of csrc/infer.cu (the window list travels as a kernel argument)
+
+
 def pack_windows(vol, out, origins, perm=(0, 1, 2), flip=(0, 0, 0), vol_index=None):
     """vol [Nv, C, D, H, W] fp32 -> out [B, d, h, w, cpad] bf16 windows of the augmented volume."""
     nv, vc, vd, vh, vw = vol.shape
     b, d, h, w, cpad = out.shape
     assert vol.dtype == torch.float32 and vol.is_contiguous() and out.is_contiguous() and len(origins) == b
-    flat = [c for o in origins for c in o]
-    with _hbm("pack_windows", b * d * h * w * (4.0 * vc + 2.0 * cpad)):
-        call("b21_pack_windows", ptr(vol), vc, vd, vh, vw, ptr(out), cpad, b, d, h, w, _iarr(flat),
-             _iarr(vol_index) if vol_index is not None else None, _iarr(perm), _iarr(flip), stream_ptr())
+    for b0 in range(0, b, MAX_WINDOWS_PER_CALL):
+        nb = min(MAX_WINDOWS_PER_CALL, b - b0)
+        flat = [c for o in origins[b0:b0 + nb] for c in o]
+        vidx = _iarr(vol_index[b0:b0 + nb]) if vol_index is not None else None
+        with _hbm("pack_windows", nb * d * h * w * (4.0 * vc + 2.0 * cpad)):
+            call("b21_pack_windows", ptr(vol), vc, vd, vh, vw, ptr(out[b0:b0 + nb]), cpad, nb, d, h, w, _iarr(flat), vidx,
+                 _iarr(perm), _iarr(flip), stream_ptr())
     return out
 
 
@@ -401,10 +407,12 @@ def blend_accumulate(logits, acc, profiles, origins, wfloor: float = 0.0):
     nwin = len(origins)
     if logits is not None:
         assert logits.shape == (nwin, k, d, h, w) and logits.is_contiguous() and logits.dtype == torch.float32
-    flat = [c for o in origins for c in o]
-    with _hbm("blend_accumulate", nwin * k * d * h * w * (12.0 if logits is not None else 8.0)):
-        call("b21_blend_accumulate", ptr(logits), ptr(acc), ptr(pd), ptr(ph), ptr(pw), nwin, k, d, h, w, ad, ah, aw,
-             _iarr(flat), float(wfloor), stream_ptr())
+    for b0 in range(0, nwin, MAX_WINDOWS_PER_CALL):
+        nb = min(MAX_WINDOWS_PER_CALL, nwin - b0)
+        flat = [c for o in origins[b0:b0 + nb] for c in o]
+        with _hbm("blend_accumulate", nb * k * d * h * w * (12.0 if logits is not None else 8.0)):
+            call("b21_blend_accumulate", ptr(logits[b0:b0 + nb]) if logits is not None else None, ptr(acc), ptr(pd),
+                 ptr(ph), ptr(pw), nb, k, d, h, w, ad, ah, aw, _iarr(flat), float(wfloor), stream_ptr())
 
 
 def tta_accumulate(acc, cnt, prob_sum, perm=(0, 1, 2), flip=(0, 0, 0), pad_before=None, apply_sigmoid=True,

@@ -78,30 +78,31 @@ def _dice(a, b):
     return 2.0 * (a & b).sum().item() / den if den else 1.0
 
 
-@pytest.mark.parametrize("ver,seed", [(2, 93), (1, 123)])
-def test_w48_batch4_128cube_graph_forward_matches_oracle(ver, seed):
+@pytest.mark.parametrize("ver,seed,batch", [(2, 93, 9), (1, 123, 4)])
+def test_w48_window_batch_graph_forward_matches_oracle(ver, seed, batch):
     """The exact code path bench.py times per window batch: pack -> forward_infer (CUDA graph; V2: folded EvoNorm on
-    levels 1-3, split level-1 concat, 128-plane marches) on 4 x 128^3 windows, vs the fp32 oracle."""
+    levels 1-3, split level-1 concat, 128-plane marches) on a batch of 128^3 windows (9 for v2_tta8, 4 for v1_sw), vs
+    the fp32 oracle."""
     from brats21_b200 import ops
     from oracle import synth
     net, params = _build(ver, seed)
-    x = torch.cat([synth.volume(seed=s, shape=ROI) for s in range(4)]).to(DEV)
+    x = torch.cat([synth.volume(seed=s, shape=ROI) for s in range(batch)]).to(DEV)
     assert ops.use_graphs and ops.use_fold and ops.fold_level3 and ops.split_concat
     with torch.no_grad():
         x8 = net.pack_input(x)
         first = net.forward_infer(x8).clone()   # warm-up + capture + first replay
         out = net.forward_infer(x8).clone()     # pure replay
         assert len(net._graphs) == 1
-        ref = torch.cat([_fwd(ver)(params, x[i:i + 1], deep_supervision=False) for i in range(4)])
+        ref = torch.cat([_fwd(ver)(params, x[i:i + 1], deep_supervision=False) for i in range(batch)])
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            auto = torch.cat([_fwd(ver)(params, x[i:i + 1], deep_supervision=False).float() for i in range(4)])
+            auto = torch.cat([_fwd(ver)(params, x[i:i + 1], deep_supervision=False).float() for i in range(batch)])
     rel, mx = _rel(out, ref), ((out - ref).abs().max() / ref.abs().max()).item()
     rel_a, mx_a = _rel(auto, ref), ((auto - ref).abs().max() / ref.abs().max()).item()
     margin = ref.abs() > MAX_ABS_TOL * ref.abs().max()
     flips = (((out >= 0) != (ref >= 0)) & margin).sum().item()
     dice = [_dice(out[:, c] >= 0, ref[:, c] >= 0) for c in range(3)]
     dice_a = [_dice(auto[:, c] >= 0, ref[:, c] >= 0) for c in range(3)]
-    _record(f"forward_v{ver}_w48_4x128", dict(
+    _record(f"forward_v{ver}_w48_{batch}x128", dict(
         rel_l2=rel, max_abs_over_max=mx, replay_vs_first_rel_l2=_rel(out, first), sign_flips_outside_margin=flips,
         dice_logit_sign=dice, torch_autocast_bf16=dict(rel_l2=rel_a, max_abs_over_max=mx_a, dice_logit_sign=dice_a),
         tol=dict(rel_l2=REL_L2_TOL, max_abs_over_max=MAX_ABS_TOL)))
@@ -110,12 +111,12 @@ def test_w48_batch4_128cube_graph_forward_matches_oracle(ver, seed):
     assert flips == 0
 
 
-@pytest.mark.parametrize("name,ver,seed,tta_name,mode", [("v2_tta8", 2, 93, "flip8", "gaussian"),
-                                                         ("v1_sw", 1, 123, None, "constant")])
-def test_full_volume_pipeline_matches_oracle(name, ver, seed, tta_name, mode):
+@pytest.mark.parametrize("name,ver,seed,tta_name,mode,sw_batch", [("v2_tta8", 2, 93, "flip8", "gaussian", 9),
+                                                                  ("v1_sw", 1, 123, None, "constant", 4)])
+def test_full_volume_pipeline_matches_oracle(name, ver, seed, tta_name, mode, sw_batch):
     """BASELINE configs 3 and 2 end to end: one synthetic 4x240x240x155 volume -> shape_to_divisible ->
-    (8 flips x) 18 windows of 128^3 in batches of 4 -> blend -> sigmoid -> mean -> threshold -> background removal ->
-    label map, exactly bench.py's step, against the oracle pipeline in fp32 on the GPU."""
+    (8 flips x) 18 windows of 128^3 in bench.py's batches (9 / 4) -> blend -> sigmoid -> mean -> threshold -> background
+    removal -> label map, exactly bench.py's step, against the oracle pipeline in fp32 on the GPU."""
     from brats21_b200 import engine, tta
     from oracle import inference as oinf
     from oracle import synth
@@ -126,7 +127,7 @@ def test_full_volume_pipeline_matches_oracle(name, ver, seed, tta_name, mode):
     assert tuple(vol.shape[2:]) == (240, 240, 160)
     comp = tta.get_flip8_transforms() if tta_name else None
     ovar = oinf.flip8_tta() if tta_name else [oinf.Variant("id", lambda x: x, lambda x: x)]
-    onehot, label, prob = engine.predict_volume([net], vol, comp, True, ROI, 4, 0.25, mode, return_prob=True)
+    onehot, label, prob = engine.predict_volume([net], vol, comp, True, ROI, sw_batch, 0.25, mode, return_prob=True)
     fwd = lambda z: _fwd(ver)(params, z.contiguous(), deep_supervision=False)  # noqa: E731
 
     def oracle_pipeline():
@@ -152,7 +153,7 @@ def test_full_volume_pipeline_matches_oracle(name, ver, seed, tta_name, mode):
     dice_auto = [_dice(hard_auto[0, c], hard_ref[0, c]) for c in range(3)]
     agree = (label == lab_ref).float().mean().item()
     _record(f"pipeline_{name}_240x240x155", dict(
-        windows=18 * len(ovar), prob_max_abs=dprob, label_bits_differing_outside_margin=mism,
+        windows=18 * len(ovar), sw_batch_size=sw_batch, prob_max_abs=dprob, label_bits_differing_outside_margin=mism,
         label_bits_differing_total=total_mism, voxels=int(prob_ref[0, 0].numel()), label_map_agreement=agree,
         dice_tc_wt_et=dice, region_voxels=[int(hard_ref[0, c].sum().item()) for c in range(3)],
         reference_logit_max_abs=logit_max,
