@@ -34,7 +34,7 @@ def main():
         vol = torch.nn.functional.pad(synth.volume(seed=1000, shape=(240, 240, 155)).to(dev), (2, 3))
         comp = tta.get_flip8_transforms() if wl == "v2_tta8" else None
         mode = "gaussian" if wl == "v2_tta8" else "constant"
-        step = lambda: engine.predict_volume([net], vol, comp, True, (128, 128, 128), 4, 0.25, mode)  # noqa: E731
+        step = lambda: engine.predict_volume([net], vol, comp, True, (128, 128, 128), 9 if wl == "v2_tta8" else 4, 0.25, mode)  # noqa: E731
     for _ in range(2):
         step()
     torch.cuda.synchronize()
