@@ -16,6 +16,10 @@
 //   * the accumulators of the CTA's taps ((kh, kw) group x 3 kd x Cin_pad fp32 columns <= 512) stay in TMEM for the whole
 //     voxel range of the CTA (split-K over the grid) and are flushed once with fp32 atomics into the torch-layout
 //     gradient [cout][cin][27].
+//   * optional (B21_WGM_MULTICAST=1, off by default — it measured slower, see the launch code): the tap groups of one
+//     voxel range form a thread-block CLUSTER (3 CTAs for the 48- and 96-channel layers), each CTA loads 1/R of the
+//     8-channel chunks and TMA-multicasts them to all R CTAs; a ring slot is released to the producers by
+//     tcgen05.commit multicast to the `empty` barrier of every CTA.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = TMEM zero-fill at start + final flush.
 // Backward of networks/equiunet2020.py:19-25 and networks/equiunet2021.py:198,201 (learning/engine.py:117 backward()).
 #include "ptx.cuh"
@@ -40,6 +44,7 @@ struct WgMarchParams {
   int G2, groups, fold;          // (kh, kw) taps per CTA, number of tap groups, max planes per MMA (N <= 256)
   int items_per_split;
   int xslots, zstages;
+  int cluster;  // CTAs per thread-block cluster (tap groups that share one voxel range): x / dz planes are TMA-multicast
   int variant;  // debug (B21_WGM_VARIANT): bit0 skip the final atomics, bit1 one K-step per tap
 };
 
@@ -87,9 +92,14 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   int i_end = i_begin + p.items_per_split;
   i_end = i_end > p.items ? p.items : i_end;
 
+  const int R = p.cluster;
+  const uint32_t crank = R > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = uint16_t((1u << R) - 1u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.xslots; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
-    for (int s = 0; s < p.zstages; ++s) { mbar_init(&zfull[s], 1); mbar_init(&zempty[s], 1); }
+    // `empty` barriers collect one tcgen05.commit arrival from EVERY CTA of the cluster: a slot may be overwritten
+    // (by multicast, in all CTAs at once) only when all of them have finished reading it
+    for (int s = 0; s < p.xslots; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], R); }
+    for (int s = 0; s < p.zstages; ++s) { mbar_init(&zfull[s], 1); mbar_init(&zempty[s], R); }
     mbar_init(&acc_bar, 1);
     mbar_init(&zero_bar, 4);
     fence_mbar_init();
@@ -102,6 +112,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (R > 1) cluster_sync_all();  // every CTA's barriers exist before the first remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -118,16 +129,27 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           mbar_wait_a(xe0 + 8u * xs, xph ^ 1);
           mbar_expect_tx_a(xf0 + 8u * xs, xtx);
           const uint32_t dst = x_addr + uint32_t(xs) * xplane_bytes;
-          for (int c = 0; c < p.kcx; ++c)
-            tma_load_5d_a(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
+          if (R > 1) {
+            for (int c = int(crank); c < p.kcx; c += R)
+              tma_load_5d_mc(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n,
+                             cmask);
+          } else {
+            for (int c = 0; c < p.kcx; ++c)
+              tma_load_5d_a(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
+          }
           if (++xs == p.xslots) { xs = 0; xph ^= 1; }
           if (j >= 2) {
             const int so = j - 2;
             mbar_wait_a(ze0 + 8u * zs, zph ^ 1);
             mbar_expect_tx_a(zf0 + 8u * zs, ztx);
             const uint32_t zd = z_addr + uint32_t(zs) * zstage_bytes;
-            for (int c = 0; c < p.kcz; ++c)
-              tma_load_5d_a(zd + c * kWMZChunk, &tmZ, zf0 + 8u * zs, c * 8, it.w0, it.h0, it.d0 + so, it.n);
+            if (R > 1) {
+              for (int c = int(crank); c < p.kcz; c += R)
+                tma_load_5d_mc(zd + c * kWMZChunk, &tmZ, zf0 + 8u * zs, c * 8, it.w0, it.h0, it.d0 + so, it.n, cmask);
+            } else {
+              for (int c = 0; c < p.kcz; ++c)
+                tma_load_5d_a(zd + c * kWMZChunk, &tmZ, zf0 + 8u * zs, c * 8, it.w0, it.h0, it.d0 + so, it.n);
+            }
             if (++zs == p.zstages) { zs = 0; zph ^= 1; }
           }
         }
@@ -140,7 +162,9 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const uint64_t dZ = umma_smem_desc(0, kWMTW * 16, kWMZChunk, kLayoutNone);
       const uint64_t dX = umma_smem_desc(0, kWMHW * 16, kWMXChunk, kLayoutNone);
       const uint32_t z_hi = uint32_t(dZ >> 32), x_hi = uint32_t(dX >> 32);
-      const uint32_t z_lo0 = uint32_t(dZ) + (z_addr >> 4), x_lo0 = uint32_t(dX) + (x_addr >> 4);
+      // (the matrix-descriptor start address is the CTA-local offset: in a cluster launch the shared-window address of
+      // a CTA carries its rank in the upper bits, which must not spill into the other descriptor fields)
+      const uint32_t z_lo0 = uint32_t(dZ) + ((z_addr & 0x3FFFFu) >> 4), x_lo0 = uint32_t(dX) + ((x_addr & 0x3FFFFu) >> 4);
       const uint32_t zstage16 = zstage_bytes >> 4, xplane16 = xplane_bytes >> 4;
       const uint32_t id1 = wgm_idesc(p.ncolx), id2 = wgm_idesc(2 * p.ncolx), id3 = wgm_idesc(3 * p.ncolx);
       int xw = 0;          // next x slot to wait for
@@ -148,6 +172,10 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       int x_lo_slot = 0;   // slot of x plane j = so (lowest plane of the current window)
       int zs = 0;
       uint32_t zph = 0;
+      auto release = [&](uint32_t bar) {  // slot free: tell the producer of every CTA in the cluster
+        if (R > 1) umma_commit_mc(bar, cmask);
+        else umma_commit_a(bar);
+      };
       mbar_wait(&zero_bar, 0);  // accumulators zeroed by the epilogue warps: every MMA accumulates
       tc_fence_after();
       for (int item = i_begin; item < i_end; ++item) {
@@ -183,15 +211,15 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             }
             j += len;
           }
-          umma_commit_a(xe0 + 8u * x_lo_slot);  // x plane j = so has served its last output plane
-          umma_commit_a(ze0 + 8u * zs);
+          release(xe0 + 8u * x_lo_slot);  // x plane j = so has served its last output plane
+          release(ze0 + 8u * zs);
           if (++x_lo_slot == p.xslots) x_lo_slot = 0;
           if (++zs == p.zstages) { zs = 0; zph ^= 1; }
         }
         // the two trailing halo planes of the item
-        umma_commit_a(xe0 + 8u * x_lo_slot);
+        release(xe0 + 8u * x_lo_slot);
         if (++x_lo_slot == p.xslots) x_lo_slot = 0;
-        umma_commit_a(xe0 + 8u * x_lo_slot);
+        release(xe0 + 8u * x_lo_slot);
         if (++x_lo_slot == p.xslots) x_lo_slot = 0;
       }
       umma_commit(&acc_bar);
@@ -232,6 +260,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (R > 1) cluster_sync_all();  // no CTA may exit while a peer can still arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -330,8 +359,30 @@ extern "C" int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, in
     B21_CUDA(cudaFuncSetAttribute(conv_wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWMSmemBudget));
     attr_set = true;
   }
+  // cluster = the tap groups of one voxel range (all of them, or three at a time when there are nine)
+  static int multicast = -1;
+  if (multicast < 0) {
+    const char* e = getenv("B21_WGM_MULTICAST");
+    // measured (profiles/r02h_wgrad_multicast_ab.md): 48x48 @128^3 0.566 -> 0.565 ms, 96x96 @64^3 0.304 -> 0.423 ms: the
+    // kernel is bound by tensor issue (M = 128 rows, cout of them useful), not by L2 -> SM traffic, and coupling the ring
+    // slots of three CTAs costs more than the saved loads.  Off by default; B21_WGM_MULTICAST=1 enables it.
+    multicast = e ? atoi(e) : 0;
+  }
+  p.cluster = 1;
+  if (multicast && p.groups > 1) p.cluster = p.groups <= 8 ? p.groups : (p.groups % 3 == 0 ? 3 : 1);
   dim3 grid(p.groups, splits);
-  conv_wgrad_march_kernel<<<grid, kWMThreads, c.smem_bytes, stream>>>(tmX, tmZ, p);
-  B21_LAUNCH_CHECK("conv_wgrad_march_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kWMThreads);
+  cfg.dynamicSmemBytes = c.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B21_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_march_kernel, tmX, tmZ, p));
   return B21_OK;
 }

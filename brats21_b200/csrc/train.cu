@@ -315,10 +315,11 @@ __global__ void __launch_bounds__(512) norm_bwd_coeffs_kernel(NormBwdArgs p) {
         const float s = p.se_scale[size_t(n) * C + c] - 1.f;
         s_du[c] = dsc * s * (1.f - s);
       }
-      for (int j = tid; j < p.hidden; j += nt) {
-        float h = p.se_b1[j];
-        for (int c = 0; c < C; ++c) h = fmaf(p.se_w1[size_t(j) * C + c], p.se_mean[size_t(n) * C + c], h);
-        s_hid[j] = fmaxf(h, 0.f);
+      for (int j = tid >> 5; j < p.hidden; j += nt >> 5) {  // one warp per hidden unit: coalesced rows of W1
+        float h = 0.f;
+        for (int c = tid & 31; c < C; c += 32) h = fmaf(p.se_w1[size_t(j) * C + c], p.se_mean[size_t(n) * C + c], h);
+        h = warp_sum(h);
+        if ((tid & 31) == 0) s_hid[j] = fmaxf(h + p.se_b1[j], 0.f);
       }
       __syncthreads();
       for (int j = tid; j < p.hidden; j += nt) {
