@@ -22,6 +22,10 @@ _SIGNATURES = {
     "b21_conv_cout_padded": [_i],
     "b21_pack_conv_weight": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b21_conv3d_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_pack_job_tap": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "b21_pack_job_march": [_vp, _vp, _i, _i, _i, _vp],
+    "b21_pack_job_slide": [_vp, _vp, _i, _i, _i, _vp],
+    "b21_pack_batch": [_vp, _i, _i, _vp],
     "b21_conv_march_supported": [_i, _i],
     "b21_conv_march_weight_bytes": [_i, _i],
     "b21_pack_conv_weight_march": [_vp, _vp, _i, _i, _i, _vp],
@@ -32,7 +36,7 @@ _SIGNATURES = {
     "b21_conv3d_slide_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv_point_supported": [_i, _i],
     "b21_conv1x1_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _vp],
-    "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _vp],
+    "b21_norm_apply": [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _f, _vp],
     "b21_channel_stats": [_vp, _i, _vp, _i, _i64, _i, _vp],
     "b21_norm_coeffs": [_i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i64, _f, _vp],
     "b21_affine_act": [_vp, _i, _vp, _i, _vp, _vp, _i, _f, _i, _i64, _i, _vp],
@@ -61,12 +65,13 @@ _SIGNATURES = {
     "b21_conv3d_wgrad": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv_wgrad_march_supported": [_i, _i],
     "b21_conv3d_wgrad_march": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "b21_norm_bwd_workspace_bytes": [_i, _i],
     "b21_norm_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                      _vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _f, _vp],
     "b21_pool_bwd": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "b21_upsample2x_bwd": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_upsample_f32_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "b21_head_conv_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp],
+    "b21_head_conv_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i64, _i, _i, _vp],
     "b21_add_inplace": [_vp, _i, _vp, _i, _i64, _i, _vp],
     "b21_dice_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _f, _f, _vp],
     "b21_dice_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _i64, _vp],
@@ -83,6 +88,14 @@ _SIGNATURES = {
     "b21_replace_rare_labels": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "b21_labels_to_channels": [_vp, _vp, _i64, _vp],
 }
+
+
+
+class PackJob(C.Structure):
+    """b21_pack_job of include/b21.h (64 bytes)."""
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("total", C.c_longlong), ("kind", _i), ("cout", _i), ("cin", _i),
+                ("tf", _i), ("p0", _i), ("p1", _i), ("p2", _i), ("p3", _i), ("blk0", _i), ("nblk", _i)]
+
 
 _lib = None
 
@@ -113,6 +126,7 @@ def load():
     lib.b21_conv_march_weight_bytes.restype = C.c_longlong
     lib.b21_conv_slide_weight_bytes.restype = C.c_longlong
     lib.b21_keep_components_workspace_bytes.restype = C.c_longlong
+    lib.b21_norm_bwd_workspace_bytes.restype = C.c_longlong
     lib.b21_replace_rare_workspace_bytes.restype = C.c_longlong
     _lib = lib
     return lib
@@ -138,7 +152,8 @@ def stream_ptr():
 # kernel launches issued per C-ABI call (host-only helpers count 0); blend launches one kernel per window
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
              "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2, "b21_ce_fwd": 2,
-             "b21_keep_components_workspace_bytes": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
+             "b21_keep_components_workspace_bytes": 0, "b21_norm_bwd_workspace_bytes": 0, "b21_pack_job_tap": 0,
+             "b21_pack_job_march": 0, "b21_pack_job_slide": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
              "b21_keep_components": 4, "b21_replace_rare_labels": 5}
 launch_count = 0
 

@@ -33,7 +33,10 @@ class GradStore:
         if missing:
             raise RuntimeError(f"parameters without a place in the backward schedule: {missing}")
         self.params = [params[n] for n in self.names]
-        total = sum(p.numel() for p in self.params)
+        # every view starts on a 16-byte boundary (the kernels that accumulate into the views use 16 B accesses); the
+        # padding elements stay zero and ride along in the all-reduce
+        pad4 = lambda k: (k + 3) // 4 * 4  # noqa: E731
+        total = sum(pad4(p.numel()) for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros((total,), dtype=torch.float32, device=dev)
         self.views: Dict[str, torch.Tensor] = {}
@@ -42,7 +45,7 @@ class GradStore:
         for n, p in zip(self.names, self.params):
             self.views[n] = self.flat[off:off + p.numel()].view(p.shape)
             self.offsets[n] = off
-            off += p.numel()
+            off += pad4(p.numel())
         # data-parallel hooks (brats21_b200.parallel.BucketReducer): start of a backward, "gradients in
         # flat[0:offset] are final", end of the backward
         self.on_begin: Optional[Callable[[], None]] = None
@@ -142,6 +145,7 @@ def _pack_train_v2(net):
     for i, conv in enumerate(net.aspp.convs):
         pk[f"aspp.convs.{i}.T"] = ops.PackedConv(conv.weight, None, transpose_flip=True)
     pk["__train__"] = True
+    net._sync_pack_table()
 
 
 def _v2_forward_train(net, x8: torch.Tensor, want_deep: bool):
@@ -244,22 +248,27 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
         se = dict(scale=t["scale"], mean=t["mean"], w1=pk[name + ".se.w1"], b1=pk[name + ".se.b1"], w2=pk[name + ".se.w2"],
                   b2=pk[name + ".se.b2"], dw1=G[pre + "6.fc.0.weight"], db1=G[pre + "6.fc.0.bias"],
                   dw2=G[pre + "6.fc.2.weight"], db2=G[pre + "6.fc.2.bias"])
+        # Order on the two streams: the data gradient (tensor-bound, on the critical path) is enqueued BEFORE the weight
+        # gradient of the same layer is released to the side stream.  Both are persistent kernels that own an SM's
+        # shared memory, so they can only run one after the other; released together (as round 1 did) the data gradient
+        # waited for the weight gradient and the HBM-bound norm adjoint that follows ran alone.  Now the weight gradient
+        # runs under the norm adjoint of the next layer (timeline: profiles/r02l_timeline_v2_train.md).
         evo_bwd(name + ".e1.g", name + ".e1.b", dy, t["z1"], t["st1"], dy, G[pre + "3.bias"], se=se)   # dy <- dz1
-        gs.on_side(lambda: ops.conv3d_wgrad(t["a0"], dy, G[pre + "3.weight"]))
         da0 = B(name + ".da0", s, c)
         ops.conv3d(dy, pk[name + ".c1.T"], out=da0)
+        gs.on_side(lambda: ops.conv3d_wgrad(t["a0"], dy, G[pre + "3.weight"]))
         evo_bwd(name + ".e0.g", name + ".e0.b", da0, t["z0"], t["st0"], da0, G[pre + "0.bias"])       # da0 <- dz0
-        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], da0, G[pre + "0.weight"]))
         if dx_out is not None:
             ops.conv3d(da0, pk[name + ".c0.T"], out=dx_out)
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], da0, G[pre + "0.weight"]))
         gs.ready(pre + "0.bias")
 
     def convevo_bwd(name, dy, dz, dx_out):
         t = tape[name]
         evo_bwd(name + ".g", name + ".b", dy, t["z"], t["st"], dz, G[name + ".conv.bias"])
-        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dz, G[name + ".conv.weight"]))
         if dx_out is not None:
             ops.conv3d(dz, pk[name + ".T"], out=dx_out)
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dz, G[name + ".conv.weight"]))
         gs.ready(name + ".conv.bias")
 
     def head_bwd(pname, x, dl, dx, scale_fold=None):
@@ -327,8 +336,8 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
     for i, dil in enumerate(net.aspp.dilations):
         dz = g_acat[..., i * q:(i + 1) * q]
         G[f"aspp.convs.{i}.bias"].add_(dz.float().sum(dim=(0, 1, 2, 3)))
-        gs.on_side(lambda dz=dz, i=i, dil=dil: ops.conv3d_wgrad(y4, dz, G[f"aspp.convs.{i}.weight"], dil=dil))
         ops.conv3d(dz, pk[f"aspp.convs.{i}.T"], out=g_y4 if i == 0 else tmp4, dil=dil)
+        gs.on_side(lambda dz=dz, i=i, dil=dil: ops.conv3d_wgrad(y4, dz, G[f"aspp.convs.{i}.weight"], dil=dil))
         if i > 0:
             ops.add_inplace(g_y4, tmp4)
         gs.ready(f"aspp.convs.{i}.bias")
@@ -431,6 +440,7 @@ def _v1_forward_train(net, x8: torch.Tensor, want_deep: bool):
             if name != "encoder1.ConvBnRelu1":
                 pk[name + ".T"] = ops.PackedConv(net.get_submodule(name).conv.weight, None, transpose_flip=True)
         pk["__train__"] = True
+        net._sync_pack_table()
     n, d, h, w, _ = x8.shape
     f = net.features
     ws = net._ws.setdefault(("v1train", n, d, h, w), {})
@@ -491,9 +501,9 @@ def _backward_v1(net, tape, dout, ddeeps, gs: GradStore):
         t = tape[name]
         ops.norm_bwd(dy, t["z"], dy, t["st"], pk[name + ".g"], pk[name + ".b"], G[name + ".bn.weight"],
                      G[name + ".bn.bias"], GN, workspace=nbw)
-        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dy, G[name + ".conv.weight"], dil=t["dil"]))
         if dx_out is not None:
             ops.conv3d(dy, pk[name + ".T"], out=dx_out, dil=t["dil"])
+        gs.on_side(lambda: ops.conv3d_wgrad(t["x"], dy, G[name + ".conv.weight"], dil=t["dil"]))  # after the dgrad: see V2
         gs.ready(name + ".conv.weight")
 
     def head_bwd(pname, x, dlog, dx, accumulate):

@@ -35,6 +35,7 @@
 #include "ptx.cuh"
 #include "fold.cuh"
 #include "host_common.h"
+#include "pack.cuh"
 #include <stdlib.h>
 
 namespace b21 {
@@ -559,23 +560,8 @@ __global__ void pack_march_weight_kernel(const float* __restrict__ w, __nv_bfloa
   const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride) {
-    const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
-    size_t t = i >> 6;
-    const int g = int(t % ng); t /= ng;
-    const int c = int(t % kc);
-    const int tap9 = int(t / kc);
-    const int n = g * 8 + n8, j = n / rows, ro = n % rows, kd = 2 - j, kh = tap9 / 3, kw = tap9 % 3;
-    const int ki = c * 8 + k8;
-    float v = 0.f;
-    if (!transpose_flip) {
-      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + (kd * 9 + kh * 3 + kw)] * (scale ? scale[ki] : 1.f);
-    } else {
-      // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
-      if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + ((2 - kd) * 9 + (2 - kh) * 3 + (2 - kw))];
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride)
+    out[i] = __float2bfloat16_rn(pack_march_value(w, i, cout_o, cin_o, rows, kc, transpose_flip, scale));
 }
 
 static inline int march_kc(int cin) { return (cin + 15) / 16 * 2; }
@@ -613,6 +599,16 @@ extern "C" int b21_pack_conv_weight_march(const float* w, void* packed, int cout
   pack_march_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, kc, transpose_flip);
   B21_LAUNCH_CHECK("pack_march_weight_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_pack_job_march(const float* w, void* packed, int cout, int cin, int transpose_flip, b21_pack_job* job) {
+  B21_CHECK_ARG(w && packed && job, "pack_job_march: null pointer");
+  const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
+  B21_CHECK_ARG(rows % 8 == 0, "pack_job_march: output channels %d must be a multiple of 8", rows);
+  job->w = w; job->out = packed; job->total = (long long)(march_wbytes(inner, rows) / 2);
+  job->kind = kPackMarch; job->cout = cout; job->cin = cin; job->tf = transpose_flip;
+  job->p0 = rows; job->p1 = march_kc(inner); job->p2 = 0; job->p3 = 0; job->blk0 = 0; job->nblk = 0;
   return B21_OK;
 }
 

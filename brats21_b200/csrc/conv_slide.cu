@@ -28,6 +28,7 @@
 #include "ptx.cuh"
 #include "fold.cuh"
 #include "host_common.h"
+#include "pack.cuh"
 #include <stdlib.h>
 
 namespace b21 {
@@ -476,24 +477,8 @@ __global__ void pack_slide_weight_kernel(const float* __restrict__ w, __nv_bfloa
   const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride) {
-    const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
-    size_t t = i >> 6;
-    const int g = int(t % ng); t /= ng;
-    const int c = int(t % kc); t /= kc;
-    const int tap = int(t % 27); t /= 27;
-    const int chunk = int(t % nchunks);
-    const int tile = int(t / nchunks);
-    const int ro = tile * nt + g * 8 + n8;
-    const int ki = (chunk * kc + c) * 8 + k8;
-    float v = 0.f;
-    if (!transpose_flip) {
-      if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap] * (scale ? scale[ki] : 1.f);
-    } else {  // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
-      if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + (26 - tap)];
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride)
+    out[i] = __float2bfloat16_rn(pack_slide_value(w, i, cout_o, cin_o, kc, nt, nchunks, transpose_flip, scale));
 }
 
 static inline int slide_nchunks(int cin) { return cin > 96 ? cin / 64 : 1; }
@@ -591,6 +576,17 @@ extern "C" int b21_pack_conv_weight_slide(const float* w, void* packed, int cout
       w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows, c.kc, c.nt, transpose_flip, nullptr, 0, 0,
       BiasTableArgs(), c.nchunks);
   B21_LAUNCH_CHECK("pack_slide_weight_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_pack_job_slide(const float* w, void* packed, int cout, int cin, int transpose_flip, b21_pack_job* job) {
+  B21_CHECK_ARG(w && packed && job, "pack_job_slide: null pointer");
+  const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
+  SlideCfg c;
+  B21_CHECK_ARG(slide_config(inner, rows, &c), "pack_job_slide: (cin %d, cout %d) unsupported", inner, rows);
+  job->w = w; job->out = packed; job->total = (long long)27 * c.nchunks * c.kc * rows * 8;
+  job->kind = kPackSlide; job->cout = cout; job->cin = cin; job->tf = transpose_flip;
+  job->p0 = rows; job->p1 = c.kc; job->p2 = c.nt; job->p3 = c.nchunks; job->blk0 = 0; job->nblk = 0;
   return B21_OK;
 }
 

@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 #include "fold.cuh"
 #include "host_common.h"
+#include "pack.cuh"
 
 namespace b21 {
 
@@ -211,19 +212,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   const size_t gstride = size_t(pack_blocks > 0 ? pack_blocks : gridDim.x) * blockDim.x;
   out += size_t(blockIdx.y) * total;
   if (scale) scale += size_t(blockIdx.y) * ldscale;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride) {
-    const int ki = int(i % inner_padded);
-    const int r = int((i / inner_padded) % rows_padded);
-    const int tap = int(i / (size_t(inner_padded) * rows_padded));
-    float v = 0.f;
-    if (!transpose_flip) {
-      if (r < cout && ki < cin) v = w[(size_t(r) * cin + ki) * T + tap] * (scale ? scale[ki] : 1.f);
-    } else {
-      // rows = original input channels, inner = original output channels, taps mirrored
-      if (r < cin && ki < cout) v = w[(size_t(ki) * cin + r) * T + (T - 1 - tap)];
-    }
-    out[i] = __float2bfloat16_rn(v);
-  }
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += gstride)
+    out[i] = __float2bfloat16_rn(pack_tap_value(w, i, cout, cin, rows_padded, inner_padded, T, transpose_flip, scale));
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -262,6 +252,19 @@ extern "C" int b21_pack_conv_weight(const float* w, void* packed, int cout, int 
   pack_conv_weight_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, transpose_flip);
   B21_LAUNCH_CHECK("pack_conv_weight_kernel");
+  return B21_OK;
+}
+
+extern "C" int b21_pack_job_tap(const float* w, void* packed, int cout, int cin, int cin_padded, int k, int transpose_flip,
+                                b21_pack_job* job) {
+  B21_CHECK_ARG(w && packed && job, "pack_job_tap: null pointer");
+  B21_CHECK_ARG(k == 1 || k == 3, "pack_job_tap: k must be 1 or 3 (got %d)", k);
+  const int rows = transpose_flip ? cin : cout, inner = transpose_flip ? cout : cin;
+  B21_CHECK_ARG(cin_padded >= inner && cin_padded % 8 == 0, "pack_job_tap: bad inner padding %d for %d", cin_padded, inner);
+  const int T = k * k * k, rows_padded = b21_conv_cout_padded(rows);
+  job->w = w; job->out = packed; job->total = (long long)T * rows_padded * cin_padded;
+  job->kind = kPackTap; job->cout = cout; job->cin = cin; job->tf = transpose_flip;
+  job->p0 = rows_padded; job->p1 = cin_padded; job->p2 = T; job->p3 = 0; job->blk0 = 0; job->nblk = 0;
   return B21_OK;
 }
 
@@ -316,11 +319,22 @@ extern "C" int b21_conv3d_fwd(const void* x, int ldx, const void* w_packed, cons
   p.tilesD = (d + td - 1) / td;
   p.chunks = (cin + 63) / 64;
   p.gsize = stats ? cout / 8 : 0;
+  // Small problems (the 16^3 level of a batch-1 training step: 32 voxel tiles): halve the N tile while the grid covers
+  // less than half of the SMs -- 384 -> 384 runs 4 x 96 columns on 128 CTAs instead of 2 x 192 on 64, 384 -> 96 runs
+  // 2 x 48 on 64 CTAs instead of 32 (the packed weight rows = ntiles * BN do not change).
+  const long long mtiles = (long long)p.tilesW * p.tilesH * p.tilesD * n;
+  const int sms = num_sms();
+  while (mtiles * ntiles * 2 < sms && p.BN % 32 == 0 && p.BN >= 64 && (!stats || (p.BN / 2) % p.gsize == 0)) {
+    p.BN /= 2;
+    ntiles *= 2;
+  }
   if (stats) B21_CHECK_ARG(cout % 8 == 0 && (p.BN % p.gsize == 0 || ntiles == 1), "conv3d_fwd: stats need whole groups per N tile");
   p.tmem_cols = 32;
   while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
   const int stage_bytes = kTapABytes + p.BN * 128;
-  int stages = (108 * 1024) / stage_bytes;
+  // two co-resident CTAs per SM when the grid has more CTAs than SMs, otherwise one CTA with a deeper ring (the K loop of
+  // a small grid is TMA-latency bound: 162 K-blocks through 3 stages measured 107 us for 21 us of MMAs)
+  int stages = ((mtiles * ntiles > sms ? 108 : 198) * 1024) / stage_bytes;
   stages = stages < 2 ? 2 : (stages > kTapMaxStages ? kTapMaxStages : stages);
   p.stages = stages;
   const size_t smem_bytes = size_t(stages) * stage_bytes + 1024;

@@ -16,6 +16,13 @@
 //   * the accumulators of the CTA's taps ((kh, kw) group x 3 kd x Cin_pad fp32 columns <= 512) stay in TMEM for the whole
 //     voxel range of the CTA (split-K over the grid) and are flushed once with fp32 atomics into the torch-layout
 //     gradient [cout][cin][27].
+//   * tap pairing (Cout <= 64): with M = 128 accumulator rows and Cout = 48 only 37.5 % of every MMA is useful work and the
+//     kernel is bound by tensor issue.  The dz plane is therefore staged TWICE, the second copy shifted by one voxel in
+//     w (A_1[u] = dz[u - e_w], TMA zero-fills u_w = 0), directly behind the first one, so that rows [Cout, 2 Cout) of the
+//     same M = 128 descriptor hold the shifted copy: sum_u dz[u - e_w][co] x[u + t - 1][ci] = dW[co][ci][t + e_w].  One MMA
+//     with the x descriptor at tap (kh, 0) updates taps (kh, 0) and (kh, 1); taps (kh, 2) use a single copy.  6 MMA sets
+//     instead of 9, 3 per CTA -> two tap groups instead of three.  The sum over u must reach u_w = W (v_w = W - 1 of the
+//     shifted copy), hence one extra, almost empty tile column: tilesW = ceil((W + 1) / 8).
 //   * optional (B21_WGM_MULTICAST=1, off by default — it measured slower, see the launch code): the tap groups of one
 //     voxel range form a thread-block CLUSTER (3 CTAs for the 48- and 96-channel layers), each CTA loads 1/R of the
 //     8-channel chunks and TMA-multicasts them to all R CTAs; a ring slot is released to the producers by
@@ -44,6 +51,9 @@ struct WgMarchParams {
   int G2, groups, fold;          // (kh, kw) taps per CTA, number of tap groups, max planes per MMA (N <= 256)
   int items_per_split;
   int xslots, zstages;
+  int pair;     // 1: dz is staged twice (second copy shifted by one voxel in w) and fills M rows [Cout, 2 Cout): one MMA
+                // updates the taps (kh, kw) and (kh, kw + 1) -- see "tap pairing" in the header comment
+  int csplit;   // input-channel halves (blockIdx.z): each CTA marches over kcx chunks = Cin_pad / csplit channels of x
   int cluster;  // CTAs per thread-block cluster (tap groups that share one voxel range): x / dz planes are TMA-multicast
   int variant;  // debug (B21_WGM_VARIANT): bit0 skip the final atomics, bit1 one K-step per tap
 };
@@ -65,6 +75,25 @@ __device__ __forceinline__ WgItem wg_decode(const WgMarchParams& p, int item) {
   return it;
 }
 
+// MMA set q of the launch -> x tap offset (kh, kw') and, when pairing, whether rows [Cout, 2 Cout) are a real tap
+struct WgSet {
+  int kh, kw;
+  bool two;
+};
+__device__ __forceinline__ WgSet wg_set(const WgMarchParams& p, int q) {
+  WgSet s;
+  if (p.pair) {
+    s.kh = q % 3;
+    s.kw = q < 3 ? 0 : 2;
+    s.two = q < 3;
+  } else {
+    s.kh = q / 3;
+    s.kw = q % 3;
+    s.two = false;
+  }
+  return s;
+}
+
 __device__ __forceinline__ uint32_t wgm_idesc(int N) {  // A and B MN-major, bf16 -> fp32, M = 128
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
 }
@@ -80,14 +109,16 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   // dz stages first: the M = 128 descriptor of a narrower dz tile reads past its end, into the x ring (valid memory;
   // those accumulator rows are never used)
   const uint32_t z_addr = smem_u32(smem);
-  const uint32_t zstage_bytes = uint32_t(p.kcz) * kWMZChunk;
+  const uint32_t zstage_bytes = uint32_t(p.kcz) * kWMZChunk * (p.pair ? 2u : 1u);
   const uint32_t x_addr = z_addr + uint32_t(p.zstages) * zstage_bytes;
   const uint32_t xplane_bytes = uint32_t(p.kcx) * kWMXChunk;
   const uint32_t xf0 = smem_u32(&xfull[0]), xe0 = smem_u32(&xempty[0]), zf0 = smem_u32(&zfull[0]), ze0 = smem_u32(&zempty[0]);
 
   const int grp = blockIdx.x;
-  const int t9_begin = grp * p.G2;
-  const int ntap = 9 - t9_begin < p.G2 ? 9 - t9_begin : p.G2;
+  const int cbase = int(blockIdx.z) * p.ncolx;  // first input channel of this CTA's share
+  const int nsets = p.pair ? 6 : 9;
+  const int t9_begin = grp * p.G2;  // first MMA set of this CTA
+  const int ntap = nsets - t9_begin < p.G2 ? nsets - t9_begin : p.G2;
   const int i_begin = blockIdx.y * p.items_per_split;
   int i_end = i_begin + p.items_per_split;
   i_end = i_end > p.items ? p.items : i_end;
@@ -121,7 +152,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (elect_one()) {
       int xs = 0, zs = 0;
       uint32_t xph = 0, zph = 0;
-      const uint32_t xtx = uint32_t(p.kcx) * kWMXData, ztx = uint32_t(p.kcz) * kWMZChunk;
+      const uint32_t xtx = uint32_t(p.kcx) * kWMXData, ztx = zstage_bytes;
       for (int item = i_begin; item < i_end; ++item) {
         const WgItem it = wg_decode(p, item);
         // order of consumption: x planes j = 0, 1, 2 | dz 0 | x 3 | dz 1 | ...
@@ -131,11 +162,11 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           const uint32_t dst = x_addr + uint32_t(xs) * xplane_bytes;
           if (R > 1) {
             for (int c = int(crank); c < p.kcx; c += R)
-              tma_load_5d_mc(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n,
+              tma_load_5d_mc(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, cbase + c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n,
                              cmask);
           } else {
             for (int c = 0; c < p.kcx; ++c)
-              tma_load_5d_a(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
+              tma_load_5d_a(dst + c * kWMXChunk, &tmX, xf0 + 8u * xs, cbase + c * 8, it.w0 - 1, it.h0 - 1, it.d0 - 1 + j, it.n);
           }
           if (++xs == p.xslots) { xs = 0; xph ^= 1; }
           if (j >= 2) {
@@ -149,6 +180,9 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             } else {
               for (int c = 0; c < p.kcz; ++c)
                 tma_load_5d_a(zd + c * kWMZChunk, &tmZ, zf0 + 8u * zs, c * 8, it.w0, it.h0, it.d0 + so, it.n);
+              if (p.pair)
+                for (int c = 0; c < p.kcz; ++c)
+                  tma_load_5d_a(zd + (p.kcz + c) * kWMZChunk, &tmZ, zf0 + 8u * zs, c * 8, it.w0 - 1, it.h0, it.d0 + so, it.n);
             }
             if (++zs == p.zstages) { zs = 0; zph ^= 1; }
           }
@@ -202,8 +236,8 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             const uint32_t xs0 = x_lo0 + uint32_t(sl) * xplane16;
             uint32_t dcol = tmem_base + uint32_t(j * p.ncolx);
             for (int t = 0; t < ntap; ++t, dcol += 3u * p.ncolx) {
-              const int t9 = t9_begin + t;
-              const uint32_t xa = xs0 + uint32_t((t9 / 3) * kWMHW + (t9 % 3));
+              const WgSet st = wg_set(p, t9_begin + t);
+              const uint32_t xa = xs0 + uint32_t(st.kh * kWMHW + st.kw);
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)  // K = 16 voxels = two h rows of the tile
                 if (ks == 0 || !(p.variant & 2))
@@ -235,21 +269,24 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     __syncwarp();
     if (lane == 0) mbar_arrive(&zero_bar);
     if (i_end > i_begin) {
-      const int co = quad * 32 + lane;
+      const int row = quad * 32 + lane;
+      const int shift = p.pair && row >= p.Cout ? 1 : 0;  // rows [Cout, 2 Cout): the copy of dz shifted in w
+      const int co = row - shift * p.Cout;
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
       for (int t = 0; t < ntap; ++t) {
-        const int t9 = t9_begin + t;
+        const WgSet st = wg_set(p, t9_begin + t);
+        const bool live = co < p.Cout && (shift == 0 || st.two);
         for (int kd = 0; kd < 3; ++kd) {
-          const int tap = kd * 9 + t9;
+          const int tap = kd * 9 + st.kh * 3 + st.kw + shift;
           for (int c0 = 0; c0 < p.ncolx; c0 += 16) {
             float v[16];
             tmem_ld16(tlane + uint32_t((t * 3 + kd) * p.ncolx + c0), v);
             tmem_ld_wait();
-            if (co < p.Cout && !(p.variant & 1)) {
+            if (live && !(p.variant & 1)) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int ci = c0 + i;
+                const int ci = cbase + c0 + i;
                 if (ci < p.Cin) atomicAdd(p.dw + (size_t(co) * p.Cin + ci) * 27 + tap, v[i]);
               }
             }
@@ -265,20 +302,37 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 struct WgMarchCfg {
-  int kcx, kcz, ncolx, G2, groups, fold, xslots, zstages;
+  int kcx, kcz, ncolx, G2, groups, fold, xslots, zstages, csplit, pair;
   size_t smem_bytes;
 };
 static bool wgm_config(int cin, int cout, WgMarchCfg* c) {
   if (cin <= 0 || cin % 8 || cin > 96 || cout <= 0 || cout % 8 || cout > 128) return false;
+  // 80-96 input channels: one tap's accumulators (3 kd x Cin columns) leave room for a single (kh, kw) tap per CTA, so
+  // nine tap groups re-read x and dz from L2.  Two input-channel halves x three taps per CTA halve that traffic.
+  static int splitting = -1;  // B21_WGM_CSPLIT=0 switches it off (A/B runs)
+  if (splitting < 0) {
+    const char* e = getenv("B21_WGM_CSPLIT");
+    splitting = e ? atoi(e) : 1;
+  }
+  c->csplit = splitting && cin >= 80 && cin % 32 == 0 ? 2 : 1;
+  cin /= c->csplit;
   c->kcx = (cin + 15) / 16 * 2;
   c->ncolx = c->kcx * 8;
   c->kcz = cout / 8;
+  static int pairing = -1;  // B21_WGM_PAIR=0 switches tap pairing off (A/B runs)
+  if (pairing < 0) {
+    const char* e = getenv("B21_WGM_PAIR");
+    pairing = e ? atoi(e) : 1;
+  }
+  c->pair = pairing && 2 * cout <= 128 ? 1 : 0;
+  const int nsets = c->pair ? 6 : 9;
   c->G2 = 512 / (3 * c->ncolx);
-  if (c->G2 > 9) c->G2 = 9;
   if (c->G2 < 1) return false;
-  c->groups = (9 + c->G2 - 1) / c->G2;
+  if (c->G2 > nsets) c->G2 = nsets;
+  if (c->pair && c->G2 < 6) c->G2 = c->G2 >= 3 ? 3 : c->G2;  // equal groups: 6 = 1 x 6 = 2 x 3 = 3 x 2 = 6 x 1 sets
+  c->groups = (nsets + c->G2 - 1) / c->G2;
   c->fold = 256 / c->ncolx > 3 ? 3 : 256 / c->ncolx;
-  const size_t xplane = size_t(c->kcx) * kWMXChunk, zstage = size_t(c->kcz) * kWMZChunk;
+  const size_t xplane = size_t(c->kcx) * kWMXChunk, zstage = size_t(c->kcz) * kWMZChunk * (c->pair ? 2 : 1);
   c->zstages = 2;
   if (size_t(kWMSmemBudget) < 128 + 2 * zstage + 4 * xplane) return false;
   size_t xs = (size_t(kWMSmemBudget) - 128 - 2 * zstage) / xplane;
@@ -317,8 +371,10 @@ extern "C" int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, in
   p.kcx = c.kcx; p.kcz = c.kcz; p.ncolx = c.ncolx;
   p.G2 = c.G2; p.groups = c.groups; p.fold = c.fold;
   p.xslots = c.xslots; p.zstages = c.zstages;
+  p.csplit = c.csplit;
+  p.pair = c.pair;
   p.tilesH = (h + kWMTH - 1) / kWMTH;
-  p.tilesW = (w + kWMTW - 1) / kWMTW;
+  p.tilesW = (w + p.pair + kWMTW - 1) / kWMTW;  // pairing: the shifted copy needs u_w = W (header comment)
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("B21_WGM_VARIANT");
@@ -327,7 +383,7 @@ extern "C" int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, in
   p.variant = variant;
   // split-K: groups x splits CTAs ~ 1 per SM; d segments so that every split gets several items
   const int sms = num_sms();
-  int splits = sms / p.groups;
+  int splits = sms / (p.groups * p.csplit);
   if (splits < 1) splits = 1;
   const long long cols = (long long)n * p.tilesH * p.tilesW;
   int segs = 1;
@@ -369,8 +425,8 @@ extern "C" int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, in
     multicast = e ? atoi(e) : 0;
   }
   p.cluster = 1;
-  if (multicast && p.groups > 1) p.cluster = p.groups <= 8 ? p.groups : (p.groups % 3 == 0 ? 3 : 1);
-  dim3 grid(p.groups, splits);
+  if (multicast && p.groups > 1 && !p.pair) p.cluster = p.groups <= 8 ? p.groups : (p.groups % 3 == 0 ? 3 : 1);
+  dim3 grid(p.groups, splits, p.csplit);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kWMThreads);

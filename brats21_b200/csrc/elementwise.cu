@@ -14,6 +14,7 @@
 #include "ptx.cuh"
 #include "fold.cuh"
 #include "host_common.h"
+#include "reduce.cuh"
 #include <stdlib.h>
 
 namespace b21 {
@@ -37,8 +38,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
                                                          __nv_bfloat16* y, int ldy,
                                                          const double* __restrict__ stats,
                                                          const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float* chan_sum, int N,
-                                                         long long nvox, int C, float eps) {
+                                                         const float* __restrict__ beta, float* chan_sum,
+                                                         int chan_slots, int N, long long nvox, int C, float eps) {
   extern __shared__ float sm[];  // a[C], b[C], csum[C]
   float* sa = sm;
   float* sb = sm + C;
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
   const long long T = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ck = int(i % chunks);  // invariant: T % chunks == 0
-  float a[8], b[8], acc[8];
+  float a[8], b[8], accv[1][8];
+  float (&acc)[8] = accv[0];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     a[j] = sa[ck * 8 + j];
@@ -123,10 +125,10 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const __nv_bfloat16* x,
     }
   }
   if (chan_sum) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&ssum[ck * 8 + j], acc[j]);
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + size_t(n) * C + c, ssum[c]);
+    block_chunk_reduce<1>(accv, chunks, C, ssum);
+    // chan_slots copies of the table: ~1200 blocks adding to the same C addresses serialise in the L2 atomic unit
+    float* cs = chan_sum + (size_t(blockIdx.x % chan_slots) * N + n) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(cs + c, ssum[c]);
   }
 }
 
@@ -564,9 +566,10 @@ using namespace b21;
 typedef __nv_bfloat16 bf16;
 
 extern "C" int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const double* stats, const float* gamma,
-                              const float* beta, float* chan_sum, int mode, int n, long long nvox, int c, float eps,
-                              void* stream) {
+                              const float* beta, float* chan_sum, int chan_slots, int mode, int n, long long nvox, int c,
+                              float eps, void* stream) {
   B21_CHECK_ARG(x && y && stats && gamma && beta, "norm_apply: null pointer");
+  B21_CHECK_ARG(!chan_sum || chan_slots >= 1, "norm_apply: chan_slots must be >= 1");
   B21_CHECK_ARG(mode == 0 || mode == 1, "norm_apply: mode must be 0 (GN+ReLU) or 1 (EvoNorm-S0)");
   B21_CHECK_ARG(c % 8 == 0 && (c / 8) >= 1 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= c && ldy >= c, "norm_apply: bad C/ld");
   B21_CHECK_ARG(n > 0 && nvox > 0, "norm_apply: empty tensor");
@@ -578,9 +581,9 @@ extern "C" int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const do
   const size_t smem = sizeof(float) * 3 * c;
   dim3 grid(gx, n);
   if (mode == 0)
-    norm_apply_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, n, nvox, c, eps);
+    norm_apply_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, chan_slots, n, nvox, c, eps);
   else
-    norm_apply_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, n, nvox, c, eps);
+    norm_apply_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, stats, gamma, beta, chan_sum, chan_slots, n, nvox, c, eps);
   B21_LAUNCH_CHECK("norm_apply_kernel");
   return B21_OK;
 }

@@ -9,6 +9,7 @@
 //   affine_act      y = act(a[n][c] * x + b[n][c]), one read + one write pass                          4 B / element
 #include "ptx.cuh"
 #include "host_common.h"
+#include "reduce.cuh"
 #include <math.h>
 
 namespace b21 {
@@ -33,8 +34,6 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16*
                                                             double* __restrict__ out, long long nvox, int C) {
   extern __shared__ float sm[];  // [2][C]
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int chunks = C >> 3;
   const long long total = nvox * chunks, T = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,7 +41,8 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16*
   const long long vstep = T / chunks;
   long long v = i / chunks;
   const __nv_bfloat16* xn = x + size_t(n) * nvox * ldx + ck * 8;
-  float s[8], q[8];
+  float sq[2][8];
+  float (&s)[8] = sq[0], (&q)[8] = sq[1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   // short fp32 runs (<= nvox / grid voxels per thread), combined in double below
@@ -55,12 +55,7 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16*
       q[j] = fmaf(f[j], f[j], q[j]);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[ck * 8 + j], s[j]);
-    atomicAdd(&sm[C + ck * 8 + j], q[j]);
-  }
-  __syncthreads();
+  block_chunk_reduce<2>(sq, chunks, C, sm);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(out + (size_t(n) * C + c) * 2, double(sm[c]));
     atomicAdd(out + (size_t(n) * C + c) * 2 + 1, double(sm[C + c]));

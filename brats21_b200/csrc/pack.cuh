@@ -1,0 +1,99 @@
+// pack.cuh — element functions of the three bf16 weight packings (generic tap layout, plane-march image, sliding-window
+// image) and the job record of the batched re-pack (b21_pack_batch: ONE launch re-packs every conv of a network after an
+// optimizer step instead of ~90 launches of 2-30 us each).  The per-layout kernels in conv_tap.cu / conv_march.cu /
+// conv_slide.cu call the same element functions, so both routes produce identical images.
+#pragma once
+#include <cuda_bf16.h>
+#include <stddef.h>
+
+namespace b21 {
+
+enum { kPackTap = 0, kPackMarch = 1, kPackSlide = 2 };
+
+// mirrors `b21_pack_job` of include/b21.h (64 bytes)
+struct PackJob {
+  const float* w;       // fp32 weight [cout][cin][k^3]
+  __nv_bfloat16* out;   // packed image
+  long long total;      // elements of the image
+  int kind, cout, cin, tf;
+  int p0, p1, p2, p3;   // tap: rows_padded, inner_padded, taps | march: rows, kc | slide: rows, kc, nt, nchunks
+  int blk0, nblk;       // block range of the job's GROUP (consecutive jobs with the same source weight share one range:
+                        // one block per 16 x 16 (cout, cin) source tile)
+};
+static_assert(sizeof(PackJob) == 64, "PackJob must match b21_pack_job");
+
+// [taps][rows_padded][inner_padded]; transpose_flip: rows = input channels, inner = output channels, taps mirrored
+__device__ __forceinline__ float pack_tap_value(const float* __restrict__ w, size_t i, int cout, int cin, int rows_padded,
+                                                int inner_padded, int T, int transpose_flip,
+                                                const float* __restrict__ scale) {
+  const int ki = int(i % inner_padded);
+  const int r = int((i / inner_padded) % rows_padded);
+  const int tap = int(i / (size_t(inner_padded) * rows_padded));
+  float v = 0.f;
+  if (!transpose_flip) {
+    if (r < cout && ki < cin) v = w[(size_t(r) * cin + ki) * T + tap] * (scale ? scale[ki] : 1.f);
+  } else {
+    if (r < cin && ki < cout) v = w[(size_t(ki) * cin + r) * T + (T - 1 - tap)];
+  }
+  return v;
+}
+
+// plane-march image [kh,kw][cin/8][3*rows/8][8][8] (conv_march.cu)
+__device__ __forceinline__ float pack_march_value(const float* __restrict__ w, size_t i, int cout_o, int cin_o, int rows,
+                                                  int kc, int transpose_flip, const float* __restrict__ scale) {
+  const int ng = 3 * rows / 8;
+  const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
+  size_t t = i >> 6;
+  const int g = int(t % ng); t /= ng;
+  const int c = int(t % kc);
+  const int tap9 = int(t / kc);
+  const int n = g * 8 + n8, j = n / rows, ro = n % rows, kd = 2 - j, kh = tap9 / 3, kw = tap9 % 3;
+  const int ki = c * 8 + k8;
+  float v = 0.f;
+  if (!transpose_flip) {
+    if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + (kd * 9 + kh * 3 + kw)] * (scale ? scale[ki] : 1.f);
+  } else {
+    // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
+    if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + ((2 - kd) * 9 + (2 - kh) * 3 + (2 - kw))];
+  }
+  return v;
+}
+
+// sliding-window image [N tile][channel chunk][tap][kc][nt/8][8][8] (conv_slide.cu)
+__device__ __forceinline__ float pack_slide_value(const float* __restrict__ w, size_t i, int cout_o, int cin_o, int kc,
+                                                  int nt, int nchunks, int transpose_flip,
+                                                  const float* __restrict__ scale) {
+  const int ng = nt / 8;
+  const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
+  size_t t = i >> 6;
+  const int g = int(t % ng); t /= ng;
+  const int c = int(t % kc); t /= kc;
+  const int tap = int(t % 27); t /= 27;
+  const int chunk = int(t % nchunks);
+  const int tile = int(t / nchunks);
+  const int ro = tile * nt + g * 8 + n8;
+  const int ki = (chunk * kc + c) * 8 + k8;
+  float v = 0.f;
+  if (!transpose_flip) {
+    if (ro < cout_o && ki < cin_o) v = w[(size_t(ro) * cin_o + ki) * 27 + tap] * (scale ? scale[ki] : 1.f);
+  } else {  // rows = original input channels, inner = original output channels, taps mirrored (data gradient)
+    if (ro < cin_o && ki < cout_o) v = w[(size_t(ki) * cin_o + ro) * 27 + (26 - tap)];
+  }
+  return v;
+}
+
+// Inverse maps: destination index of source element (co, ci, tap) in each image (used by the batched re-pack, which
+// walks the SOURCE in coalesced tiles).  r / ki are the image's row / inner channel (swapped for transpose_flip).
+__device__ __forceinline__ size_t pack_tap_index(int r, int ki, int tap, int rows_padded, int inner_padded) {
+  return (size_t(tap) * rows_padded + r) * inner_padded + ki;
+}
+__device__ __forceinline__ size_t pack_march_index(int ro, int ki, int kd, int kh, int kw, int rows, int kc) {
+  const int ng = 3 * rows / 8, n = (2 - kd) * rows + ro;
+  return (((size_t(kh * 3 + kw) * kc + (ki >> 3)) * ng + (n >> 3)) * 8 + (n & 7)) * 8 + (ki & 7);
+}
+__device__ __forceinline__ size_t pack_slide_index(int ro, int ki, int tap, int kc, int nt, int nchunks) {
+  const int ng = nt / 8, tile = ro / nt, rem = ro - tile * nt, q = ki >> 3, chunk = q / kc, c = q - chunk * kc;
+  return (((((size_t(tile) * nchunks + chunk) * 27 + tap) * kc + c) * ng + (rem >> 3)) * 8 + (rem & 7)) * 8 + (ki & 7);
+}
+
+}  // namespace b21

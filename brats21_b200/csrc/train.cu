@@ -12,6 +12,7 @@
 // so that a thread keeps the same 8 channels for its whole grid-stride loop (per-channel partial sums in registers).
 #include "ptx.cuh"
 #include "host_common.h"
+#include "reduce.cuh"
 
 namespace b21 {
 
@@ -176,25 +177,26 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
 // MODE 1: y = z sigmoid(z) r gamma + beta          (EvoNorm3D-S0), optionally followed by out = y * sc[n][c]
 // reduce: per (n, c)   R1 = sum dyA,  R2 = sum dyA * u,  R3 = sum u
 //         MODE 0: dyA = dy * [y > 0], u = z ;  MODE 1: dyA = dy, u = z sigmoid(z)
+constexpr int kRedSlots = 32;  // copies of the reduction table (norm_bwd_reduce), folded by norm_bwd_coeffs
+constexpr int kColSlots = 16;  // copies of the bias-gradient row (norm_bwd_apply), folded by its last block
 struct NormFwdCoef {  // how the forward pass maps z to y for channel c of sample n: y = u * a + b (MODE 1) / z*a+b (0)
   float a, b;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+__global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                               const __nv_bfloat16* __restrict__ z, int ldz,
                                                               const float* __restrict__ fa, const float* __restrict__ fb,
                                                               double* __restrict__ red, long long nvox, int C) {
-  extern __shared__ float sm[];  // [3][C]
+  extern __shared__ float sm[];  // [3][C] block sums, filled by block_chunk_reduce<3>
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int chunks = C >> 3;
   const long long total = nvox * chunks;
   const long long T = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ck = int(i % chunks);
-  float a[8], b[8], r1[8], r2[8], r3[8];
+  float a[8], b[8], rr[3][8];
+  float (&r1)[8] = rr[0], (&r2)[8] = rr[1], (&r3)[8] = rr[2];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     a[j] = MODE == 0 ? fa[size_t(n) * C + ck * 8 + j] : 0.f;
@@ -239,22 +241,20 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const __nv_bfloat1
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[ck * 8 + j], r1[j]);
-    atomicAdd(&sm[C + ck * 8 + j], r2[j]);
-    atomicAdd(&sm[2 * C + ck * 8 + j], r3[j]);
-  }
-  __syncthreads();
+  block_chunk_reduce<3>(rr, chunks, C, sm);
+  // kRedSlots copies of the table: ~1200 blocks adding to the same 3*C addresses serialise in the L2 atomic unit
+  // (measured 75 us per launch, whatever the tensor size); with 32 slots a launch sees < 40 adds per address
+  double* rs = red + (size_t(blockIdx.x % kRedSlots) * gridDim.y + n) * C * 3;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
-    for (int q = 0; q < 3; ++q) atomicAdd(red + (size_t(n) * C + c) * 3 + q, double(sm[q * C + c]));
+    for (int q = 0; q < 3; ++q) atomicAdd(rs + size_t(c) * 3 + q, double(sm[q * C + c]));
 }
 
 // One block.  From the reductions, the forward statistics and (optionally) the squeeze-excite state, produce the
 // per-(n, c) coefficient table of the apply pass   dz = (dy * p0 + p1) * D(z) - p2 * z + p3
 // (D = swish' for MODE 1, the ReLU mask for MODE 0) and ACCUMULATE the parameter gradients.
 struct NormBwdArgs {
-  const double* red;      // [N][C][3]
+  const double* red;      // [N][C][3] (copy 0 of redw after the fold)
+  double* redw;           // [kRedSlots][N][C][3] as written by norm_bwd_reduce
   const double* stats;    // forward statistics, double[SLOTS][N][8][2]
   const float* gamma;     // [C]
   const float* beta;      // [C]
@@ -273,6 +273,47 @@ struct NormBwdArgs {
   float eps;
 };
 
+// One block:  y[n] = sum_m M[m][n] x[m]   and   dM[m][n] += x[m] * z[n]    (M, dM row-major [rows][cols], cols % 4 == 0;
+// x, y in shared memory, z anywhere).  Thread t owns four columns and every S-th row: its accumulators live in
+// registers, loads are 16 B and independent (a thread per output looping over a whole row / column of a 384 x 192
+// matrix took 30 us, shared-memory float atomics -- compare-and-swap loops -- 270 us).  part: blockDim.x * 4 floats.
+__device__ __forceinline__ void matvec_t_outer(const float* __restrict__ M, float* dM, const float* x, const float* z,
+                                               float* y, float* part, int rows, int cols) {
+  const int tid = threadIdx.x, q = cols >> 2;
+  int S = int(blockDim.x) / q;
+  if (S > rows) S = rows;
+  if (S < 1) S = 1;  // cols > 4 * blockDim.x: column groups are walked in passes
+  for (int g0 = 0; g0 < q; g0 += int(blockDim.x)) {
+    const int g = g0 + (S > 1 ? tid % q : tid), slice = S > 1 ? tid / q : 0;
+    const bool on = g < q && slice < S;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      const float4 zv = make_float4(z[4 * g], z[4 * g + 1], z[4 * g + 2], z[4 * g + 3]);
+#pragma unroll 4
+      for (int m = slice; m < rows; m += S) {
+        const size_t off = size_t(m) * cols + 4 * g;
+        const float4 w = *reinterpret_cast<const float4*>(M + off);
+        float4 d = *reinterpret_cast<const float4*>(dM + off);
+        const float xm = x[m];
+        acc.x = fmaf(w.x, xm, acc.x); acc.y = fmaf(w.y, xm, acc.y); acc.z = fmaf(w.z, xm, acc.z); acc.w = fmaf(w.w, xm, acc.w);
+        d.x = fmaf(xm, zv.x, d.x); d.y = fmaf(xm, zv.y, d.y); d.z = fmaf(xm, zv.z, d.z); d.w = fmaf(xm, zv.w, d.w);
+        *reinterpret_cast<float4*>(dM + off) = d;
+      }
+      if (S == 1) { y[4 * g] = acc.x; y[4 * g + 1] = acc.y; y[4 * g + 2] = acc.z; y[4 * g + 3] = acc.w; }
+    }
+    if (S > 1) {  // (then q <= blockDim.x and there is a single pass)
+      if (on) *reinterpret_cast<float4*>(part + 4 * (slice * q + g)) = acc;
+      __syncthreads();
+      for (int n = tid; n < cols; n += blockDim.x) {
+        float t = 0.f;
+        for (int sl = 0; sl < S; ++sl) t += part[4 * (sl * q + (n >> 2)) + (n & 3)];
+        y[n] = t;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512) norm_bwd_coeffs_kernel(NormBwdArgs p) {
   extern __shared__ float sm[];  // mu[8], r[8], A[8], B[8], then per-channel scratch: dsc[C], du[C], hid[H], dh[H], dm[C]
@@ -284,8 +325,19 @@ __global__ void __launch_bounds__(512) norm_bwd_coeffs_kernel(NormBwdArgs p) {
   float* s_hid = s_du + p.C;
   float* s_dh = s_hid + p.hidden;
   float* s_dm = s_dh + p.hidden;
+  float* s_part = s_dm + p.C;  // blockDim.x * 4 floats (squeeze-excite only)
   const int C = p.C, gsz = C / 8, tid = threadIdx.x, nt = blockDim.x;
   const double cnt = double(p.nvox) * gsz;
+  {  // fold the kRedSlots copies of the reduction table into copy 0
+    const int tot = p.N * C * 3;
+    for (int i = tid; i < tot; i += nt) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int slot = 0; slot < kRedSlots; ++slot) s += p.redw[size_t(slot) * tot + i];
+      p.redw[i] = s;
+    }
+    __syncthreads();
+  }
   for (int n = 0; n < p.N; ++n) {
     if (tid < 8) {
       double s = 0.0, q = 0.0;
@@ -322,28 +374,18 @@ __global__ void __launch_bounds__(512) norm_bwd_coeffs_kernel(NormBwdArgs p) {
         if ((tid & 31) == 0) s_hid[j] = fmaxf(h + p.se_b1[j], 0.f);
       }
       __syncthreads();
+      // dW2[c][j] += du[c] * hid[j] ; dh_raw[j] = sum_c W2[c][j] du[c]
+      matvec_t_outer(p.se_w2, p.d_w2, s_du, s_hid, s_dh, s_part, C, p.hidden);
+      for (int c = tid; c < C; c += nt) p.d_b2[c] += s_du[c];
       for (int j = tid; j < p.hidden; j += nt) {
-        float d = 0.f;
-        for (int c = 0; c < C; ++c) d = fmaf(p.se_w2[size_t(c) * p.hidden + j], s_du[c], d);
-        d = s_hid[j] > 0.f ? d : 0.f;
+        const float d = s_hid[j] > 0.f ? s_dh[j] : 0.f;
         s_dh[j] = d;
         p.d_b1[j] += d;
       }
-      for (int i = tid; i < C * p.hidden; i += nt) {  // dW2[c][j] += du[c] * hid[j]
-        const int c = i / p.hidden, j = i - c * p.hidden;
-        p.d_w2[i] += s_du[c] * s_hid[j];
-      }
-      for (int c = tid; c < C; c += nt) p.d_b2[c] += s_du[c];
       __syncthreads();
-      for (int i = tid; i < p.hidden * C; i += nt) {  // dW1[j][c] += dh[j] * mean[c]
-        const int j = i / C, c = i - j * C;
-        p.d_w1[i] += s_dh[j] * p.se_mean[size_t(n) * C + c];
-      }
-      for (int c = tid; c < C; c += nt) {
-        float d = 0.f;
-        for (int j = 0; j < p.hidden; ++j) d = fmaf(p.se_w1[size_t(j) * C + c], s_dh[j], d);
-        s_dm[c] = d / float(p.nvox);  // gradient of every voxel of channel c through the mean
-      }
+      // dW1[j][c] += dh[j] * mean[c] ; dm[c] = sum_j W1[j][c] dh[j]
+      matvec_t_outer(p.se_w1, p.d_w1, s_dh, p.se_mean + size_t(n) * C, s_dm, s_part, p.hidden, C);
+      for (int c = tid; c < C; c += nt) s_dm[c] /= float(p.nvox);  // gradient of every voxel of channel c through the mean
       __syncthreads();
     }
     // per-channel sums of the gradient w.r.t. the norm output y: dyE = dy * sc + dmv
@@ -422,17 +464,17 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ z, int ldz,
                                                              __nv_bfloat16* dz, int lddz, const float* __restrict__ coef,
                                                              const float* __restrict__ fa, const float* __restrict__ fb,
-                                                             float* colsum, long long nvox, int C) {
+                                                             float* colsum, float* cs_ws, unsigned int* cs_count,
+                                                             long long nvox, int C) {
   extern __shared__ float sm[];  // [C] column sums
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int chunks = C >> 3;
   const long long total = nvox * chunks;
   const long long T = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ck = int(i % chunks);
-  float p0[8], p1[8], p2[8], p3[8], a[8], b[8], acc[8];
+  float p0[8], p1[8], p2[8], p3[8], a[8], b[8], accv[1][8];
+  float (&acc)[8] = accv[0];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float* co = coef + (size_t(n) * C + ck * 8 + j) * 4;
@@ -489,10 +531,24 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const __nv_bfloat16
     }
   }
   if (colsum) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sm[ck * 8 + j], acc[j]);
+    block_chunk_reduce<1>(accv, chunks, C, sm);
+    // kColSlots copies of the row (see norm_bwd_reduce); the last block to finish folds them into colsum
+    float* cs = cs_ws + size_t(blockIdx.x % kColSlots) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(cs + c, sm[c]);
+    __shared__ bool last;
+    __threadfence();
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(colsum + c, sm[c]);
+    if (threadIdx.x == 0) last = atomicAdd(cs_count, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int slot = 0; slot < kColSlots; ++slot) t += __ldcg(cs_ws + size_t(slot) * C + c);
+        colsum[c] += t;
+      }
+    }
   }
 }
 
@@ -664,11 +720,9 @@ __global__ void __launch_bounds__(256) head_conv_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ scale, const float* __restrict__ w,
                                                             const float* __restrict__ dl, __nv_bfloat16* __restrict__ dx,
                                                             int lddx, int accumulate, float* __restrict__ dws,
-                                                            float* __restrict__ db, long long nvox, int C) {
+                                                            float* __restrict__ db, int slots, long long nvox, int C) {
   extern __shared__ float sm[];  // [K][C] partial dws + [K] db
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < K * C + K; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int chunks = C >> 3;
   const long long total = nvox * chunks;
   const long long T = (long long)gridDim.x * blockDim.x;
@@ -710,15 +764,21 @@ __global__ void __launch_bounds__(256) head_conv_bwd_kernel(const __nv_bfloat16*
     }
     *reinterpret_cast<uint4*>(dxn + v * lddx + ck * 8) = pack8t(o);
   }
+  block_chunk_reduce<K>(acc, chunks, C, sm);
+  // bias gradient: warp sums first (only the ck == 0 threads hold non-zero values), then <= 8 adds per address
+  if (threadIdx.x < K) sm[K * C + threadIdx.x] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sm[k * C + ck * 8 + j], acc[k][j]);
-    if (ck == 0) atomicAdd(&sm[K * C + k], accb[k]);
+    const float t = warp_sum(accb[k]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sm[K * C + k], t);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < K * C; c += blockDim.x) atomicAdd(dws + size_t(n) * K * C + c, sm[c]);
-  if (threadIdx.x < K) atomicAdd(db + threadIdx.x, sm[K * C + threadIdx.x]);
+  // `slots` copies of the tables (the caller sums them): ~1200 blocks adding to K * C addresses serialise in L2
+  const int slot = blockIdx.x % slots;
+  float* dst = dws + (size_t(slot) * gridDim.y + n) * K * C;
+  for (int c = threadIdx.x; c < K * C; c += blockDim.x) atomicAdd(dst + c, sm[c]);
+  if (threadIdx.x < K) atomicAdd(db + slot * K + threadIdx.x, sm[K * C + threadIdx.x]);
 }
 
 // dst += src  (channels-last bf16 with channel strides)
@@ -793,6 +853,12 @@ extern "C" int b21_dice_bwd(const float* logits, const float* target, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ norm backward
+extern "C" long long b21_norm_bwd_workspace_bytes(int n, int c) {
+  if (n <= 0 || c <= 0) return 0;
+  return (long long)(size_t(kRedSlots) * n * c * 3 * sizeof(double) + size_t(kColSlots) * c * sizeof(float) + 16 +
+                     size_t(n) * c * 6 * sizeof(float));
+}
+
 extern "C" int b21_norm_bwd(const void* dy, int lddy, const void* z, int ldz, void* dz, int lddz, const double* stats,
                             const float* gamma, const float* beta, float* dgamma, float* dbeta, float* colsum,
                             const float* se_scale, const float* se_mean, const float* se_w1, const float* se_b1,
@@ -805,15 +871,19 @@ extern "C" int b21_norm_bwd(const void* dy, int lddy, const void* z, int ldz, vo
   B21_CHECK_ARG(!(mode == 0 && se_w1), "norm_bwd: squeeze-excite only follows EvoNorm");
   B21_CHECK_ARG(!se_w1 || (se_scale && se_mean && se_b1 && se_w2 && se_b2 && d_w1 && d_b1 && d_w2 && d_b2 && hidden > 0),
                 "norm_bwd: incomplete squeeze-excite arguments");
-  // workspace: red double[n][c][3] | coef float[n][c][4] | fa float[n][c] | fb float[n][c]
-  const size_t need = size_t(n) * c * (3 * sizeof(double) + 6 * sizeof(float));
+  // workspace: red double[kRedSlots][n][c][3] | cs float[kColSlots][c] | counter (16 B) | coef float[n][c][4] |
+  //            fa float[n][c] | fb float[n][c]        (the first three are zeroed by ONE memset per call)
+  const size_t need = (size_t)b21_norm_bwd_workspace_bytes(n, c);
   B21_CHECK_ARG((size_t)workspace_bytes >= need, "norm_bwd: workspace too small (%lld < %zu)", workspace_bytes, need);
+  B21_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "norm_bwd: workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   double* red = reinterpret_cast<double*>(workspace);
-  float* coef = reinterpret_cast<float*>(red + size_t(n) * c * 3);
+  float* cs_ws = reinterpret_cast<float*>(red + size_t(kRedSlots) * n * c * 3);
+  unsigned int* cs_count = reinterpret_cast<unsigned int*>(cs_ws + size_t(kColSlots) * c);
+  float* coef = reinterpret_cast<float*>(cs_count + 4);
   float* fa = coef + size_t(n) * c * 4;
   float* fb = fa + size_t(n) * c;
-  B21_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * n * c * 3, st));
+  B21_CUDA(cudaMemsetAsync(red, 0, sizeof(double) * kRedSlots * n * c * 3 + sizeof(float) * kColSlots * c + 16, st));
   const int chunks = c / 8;
   dim3 grid(chunk_grid(nvox, chunks, n), n);
   if (mode == 0) {
@@ -823,18 +893,18 @@ extern "C" int b21_norm_bwd(const void* dy, int lddy, const void* z, int ldz, vo
     norm_bwd_reduce_kernel<1><<<grid, 256, sizeof(float) * 3 * c, st>>>((const bf16*)dy, lddy, (const bf16*)z, ldz, fa, fb, red, nvox, c);
   }
   NormBwdArgs a;
-  a.red = red; a.stats = stats; a.gamma = gamma; a.beta = beta; a.fa = fa; a.fb = fb; a.coef = coef;
+  a.red = red; a.redw = red; a.stats = stats; a.gamma = gamma; a.beta = beta; a.fa = fa; a.fb = fb; a.coef = coef;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.se_scale = se_scale; a.se_mean = se_mean; a.se_w1 = se_w1; a.se_b1 = se_b1; a.se_w2 = se_w2; a.se_b2 = se_b2;
   a.d_w1 = d_w1; a.d_b1 = d_b1; a.d_w2 = d_w2; a.d_b2 = d_b2;
   a.N = n; a.C = c; a.hidden = se_w1 ? hidden : 0; a.nvox = nvox; a.eps = eps;
-  const size_t smc = sizeof(float) * (32 + 2 * c + 2 * a.hidden);
+  const size_t smc = sizeof(float) * (32 + 2 * c + 2 * a.hidden + (a.hidden ? 512 * 4 : 0));
   if (mode == 0) norm_bwd_coeffs_kernel<0><<<1, 512, smc, st>>>(a);
   else norm_bwd_coeffs_kernel<1><<<1, 512, smc, st>>>(a);
   if (mode == 0)
-    norm_bwd_apply_kernel<0><<<grid, 256, sizeof(float) * c, st>>>((const bf16*)dy, lddy, (const bf16*)z, ldz, (bf16*)dz, lddz, coef, fa, fb, colsum, nvox, c);
+    norm_bwd_apply_kernel<0><<<grid, 256, sizeof(float) * c, st>>>((const bf16*)dy, lddy, (const bf16*)z, ldz, (bf16*)dz, lddz, coef, fa, fb, colsum, cs_ws, cs_count, nvox, c);
   else
-    norm_bwd_apply_kernel<1><<<grid, 256, sizeof(float) * c, st>>>((const bf16*)dy, lddy, (const bf16*)z, ldz, (bf16*)dz, lddz, coef, fa, fb, colsum, nvox, c);
+    norm_bwd_apply_kernel<1><<<grid, 256, sizeof(float) * c, st>>>((const bf16*)dy, lddy, (const bf16*)z, ldz, (bf16*)dz, lddz, coef, fa, fb, colsum, cs_ws, cs_count, nvox, c);
   B21_LAUNCH_CHECK("norm_bwd kernels");
   return B21_OK;
 }
@@ -869,15 +939,16 @@ extern "C" int b21_upsample_f32_bwd(const float* dy, float* dx, int planes, int 
 }
 
 extern "C" int b21_head_conv_bwd(const void* x, int ldx, const float* scale, const float* w, const float* dl, void* dx,
-                                 int lddx, int accumulate, float* dws, float* db, int n, long long nvox, int c, int k,
-                                 void* stream) {
+                                 int lddx, int accumulate, float* dws, float* db, int slots, int n, long long nvox, int c,
+                                 int k, void* stream) {
   B21_CHECK_ARG(x && w && dl && dx && dws && db, "head_conv_bwd: null pointer");
-  B21_CHECK_ARG(k >= 1 && k <= 4 && c % 8 == 0 && c <= 1024, "head_conv_bwd: K 1..4, C multiple of 8");
+  B21_CHECK_ARG(k >= 1 && k <= 4 && c % 8 == 0 && c <= 1024, "head_conv_bwd: K 1..4, C multiple of 8, C <= 1024");
+  B21_CHECK_ARG(slots >= 1, "head_conv_bwd: slots must be >= 1");
   const int chunks = c / 8;
   dim3 grid(chunk_grid(nvox, chunks, n, 2), n);
   const size_t smem = sizeof(float) * (k * c + k);
   cudaStream_t st = (cudaStream_t)stream;
-#define B21_HEAD_BWD(KK) head_conv_bwd_kernel<KK><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, dl, (bf16*)dx, lddx, accumulate, dws, db, nvox, c)
+#define B21_HEAD_BWD(KK) head_conv_bwd_kernel<KK><<<grid, 256, smem, st>>>((const bf16*)x, ldx, scale, w, dl, (bf16*)dx, lddx, accumulate, dws, db, slots, nvox, c)
   switch (k) {
     case 1: B21_HEAD_BWD(1); break;
     case 2: B21_HEAD_BWD(2); break;

@@ -92,13 +92,36 @@ class PackedConv:
             call("b21_border_weight_sums", ptr(self.w32), ptr(self._fold["ws"]), self.cout, self.cin_true, self.taps,
                  stream_ptr())
 
-    def refresh(self):
-        """Re-pack after the source parameters changed in place (same storage): buffers are re-used."""
-        if self.w32.data_ptr() != self._src_w.data_ptr():  # the fp32 view was a converted copy: bring it up to date
+    def sync_sources(self):
+        """Bring the fp32 views up to date when they are converted copies (parameters that are not fp32 / contiguous)."""
+        if self.w32.data_ptr() != self._src_w.data_ptr():
             self.w32.copy_(self._src_w.detach())
         if self.bias is not None and self.bias.data_ptr() != self._src_b.data_ptr():
             self.bias.copy_(self._src_b.detach())
+
+    def refresh(self):
+        """Re-pack after the source parameters changed in place (same storage): buffers are re-used."""
+        self.sync_sources()
         self._launch_packs()
+
+    def pack_jobs(self):
+        """Job records of b21_pack_batch that reproduce _launch_packs (without the fold's border sums)."""
+        import ctypes as C
+        cout, cin = self._wshape
+        tf = int(self._tf)
+        jobs = []
+
+        def add(fn, *args):
+            job = _lib.PackJob()
+            call(fn, *args, C.addressof(job))
+            jobs.append(job)
+
+        add("b21_pack_job_tap", ptr(self.w32), ptr(self.w), cout, cin, self.cin_padded, self.k, tf)
+        if self.w_march is not None:
+            add("b21_pack_job_march", ptr(self.w32), ptr(self.w_march), cout, cin, tf)
+        if self.w_slide is not None:
+            add("b21_pack_job_slide", ptr(self.w32), ptr(self.w_slide), cout, cin, tf)
+        return jobs
 
 
 def new_stats(n: int, device) -> torch.Tensor:
@@ -284,14 +307,28 @@ wgrad_side_stream = True
 GN_RELU, EVO_S0 = 0, 1
 
 
+CHAN_SLOTS = 16
+_chan_slots = {}
+
+
 def norm_apply(x, stats, gamma, beta, mode, out=None, chan_sum=None, eps=1e-5):
-    """GroupNorm(8)+ReLU or EvoNorm-S0 from conv-epilogue statistics; in place when out is None."""
+    """GroupNorm(8)+ReLU or EvoNorm-S0 from conv-epilogue statistics; in place when out is None.  chan_sum (fp32 [n, c])
+    RECEIVES the per-channel sums of the outputs (the kernel spreads its atomics over CHAN_SLOTS copies)."""
     n, d, h, w, c = x.shape
     if out is None:
         out = x
+    slots = None
+    if chan_sum is not None:
+        key = (n, c, x.device)
+        slots = _chan_slots.get(key)
+        if slots is None:
+            slots = _chan_slots[key] = torch.empty((CHAN_SLOTS, n, c), dtype=torch.float32, device=x.device)
+        slots.zero_()
     with _hbm("norm_apply", 4.0 * n * d * h * w * c):
-        call("b21_norm_apply", ptr(x), _ld(x), ptr(out), _ld(out), ptr(stats), ptr(gamma), ptr(beta), ptr(chan_sum),
-             mode, n, d * h * w, c, eps, stream_ptr())
+        call("b21_norm_apply", ptr(x), _ld(x), ptr(out), _ld(out), ptr(stats), ptr(gamma), ptr(beta), ptr(slots),
+             CHAN_SLOTS, mode, n, d * h * w, c, eps, stream_ptr())
+    if slots is not None:
+        torch.sum(slots, dim=0, out=chan_sum)
     return out
 
 
@@ -496,7 +533,7 @@ def conv3d_wgrad(x, dz, dw, dil: int = 1):
 
 
 def norm_bwd_workspace(n, c, device):
-    return torch.empty((n * c * 48,), dtype=torch.uint8, device=device)
+    return torch.empty((int(_lib.load().b21_norm_bwd_workspace_bytes(n, c)),), dtype=torch.uint8, device=device)
 
 
 def norm_bwd(dy, z, dz, stats, gamma, beta, dgamma, dbeta, mode, colsum=None, se=None, workspace=None, eps=1e-5):
@@ -540,11 +577,12 @@ def head_conv_bwd(x, weight, dl, dx, scale=None, accumulate=False):
     """Returns (dws [n, k, c], db [k]); writes/accumulates dx (bf16)."""
     n, d, h, w, c = x.shape
     k = weight.shape[0]
-    dws = torch.zeros((n, k, c), dtype=torch.float32, device=x.device)
-    db = torch.zeros((k,), dtype=torch.float32, device=x.device)
+    # CHAN_SLOTS copies of both tables (block b adds to copy b % slots), summed below
+    dws_t = torch.zeros((CHAN_SLOTS, n, k, c), dtype=torch.float32, device=x.device)
+    db_t = torch.zeros((CHAN_SLOTS, k), dtype=torch.float32, device=x.device)
     call("b21_head_conv_bwd", ptr(x), _ld(x), ptr(scale), ptr(weight), ptr(dl.contiguous()), ptr(dx), _ld(dx),
-         int(accumulate), ptr(dws), ptr(db), n, d * h * w, c, k, stream_ptr())
-    return dws, db
+         int(accumulate), ptr(dws_t), ptr(db_t), CHAN_SLOTS, n, d * h * w, c, k, stream_ptr())
+    return dws_t.sum(0), db_t.sum(0)
 
 
 def add_inplace(dst, src):

@@ -80,6 +80,28 @@ int b21_pack_conv_weight_slide(const float* w, void* packed, int cout, int cin, 
 int b21_conv3d_slide_fwd(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,
                          double* stats, int n, int d, int h, int w, int cin, int cout, void* stream);
 
+/* Batched re-pack: after an optimizer step every conv weight of a network is re-packed (generic, plane-march and
+ * sliding-window images, forward and transposed) -- ~90 launches of 2-30 us.  b21_pack_job_{tap,march,slide} fill one
+ * HOST job record each (same arguments and layout rules as the matching b21_pack_conv_weight* call).  The caller
+ * orders the records so that jobs with the same source `w` are consecutive (a group), gives every job of a group the
+ * same block range blk0 / nblk = ceil(cout/16) * ceil(cin/16) (one block per 16 x 16 source tile; groups in ascending
+ * blk0), copies the records to the device once and then calls b21_pack_batch: ONE launch of `total_blocks` blocks x 256
+ * threads reads every source tile once and rewrites the valid elements of all its images (identical to the single
+ * calls; padding rows / channels, zeroed by the single calls, are not touched). */
+typedef struct b21_pack_job {
+  const void* w;    /* fp32 weight [cout][cin][k^3] (device) */
+  void* out;        /* packed bf16 image (device) */
+  long long total;  /* elements of the image */
+  int kind, cout, cin, tf;
+  int p0, p1, p2, p3;
+  int blk0, nblk;   /* block range of the job's group, set by the caller */
+} b21_pack_job;
+int b21_pack_job_tap(const float* w, void* packed, int cout, int cin, int cin_padded, int k, int transpose_flip,
+                     b21_pack_job* job);
+int b21_pack_job_march(const float* w, void* packed, int cout, int cin, int transpose_flip, b21_pack_job* job);
+int b21_pack_job_slide(const float* w, void* packed, int cout, int cin, int transpose_flip, b21_pack_job* job);
+int b21_pack_batch(const b21_pack_job* jobs_dev, int njobs, int total_blocks, void* stream);
+
 /* Persistent 1x1x1 variant of b21_conv3d_fwd (taps = 1) for the HBM-bound ConvEvo bridges / up-convs
  * (networks/equiunet2021.py:214-222,262-269): weights resident in shared memory, activation tiles streamed through a
  * TMA ring, double-buffered TMEM accumulator.  x / y are [n][nvox][ld] bf16; `w_packed` is the k = 1 packing of
@@ -136,11 +158,12 @@ int b21_affine_pool(const void* x, int ldx, const float* a_in, const float* b_in
 /* ------------------------------------------------------------------------------------- normalisation / SE
  * norm_apply: y = GroupNorm(8,C)(x) -> ReLU (mode 0; networks/factory.py:182 + equiunet2020.py:60-61) or
  * EvoNorm3D-S0 (mode 1; networks/equiunet2021.py:48-52,95-105: x*sigmoid(x)/sqrt(var_unbiased+eps)*gamma+beta)
- * from the statistics buffer b21_conv3d_fwd filled.  x may alias y.  If chan_sum != NULL (fp32 [n][c], zeroed by
- * the caller) the per-channel sums of the outputs are accumulated into it (squeeze-excite mean). */
+ * from the statistics buffer b21_conv3d_fwd filled.  x may alias y.  If chan_sum != NULL (fp32 [chan_slots][n][c],
+ * zeroed by the caller) the per-channel sums of the outputs are accumulated into it (squeeze-excite mean): block b adds
+ * to copy b % chan_slots (one copy makes ~1200 blocks serialise on c addresses); the caller sums the copies. */
 int b21_norm_apply(const void* x, int ldx, void* y, int ldy, const double* stats, const float* gamma,
-                   const float* beta, float* chan_sum, int mode, int n, long long nvox, int c, float eps,
-                   void* stream);
+                   const float* beta, float* chan_sum, int chan_slots, int mode, int n, long long nvox, int c,
+                   float eps, void* stream);
 
 /* The rest of the norm / activation factory of EquiUnet (networks/factory.py:179-200: get_norm_layer "instance" =
  * nn.InstanceNorm3d(affine), "batch" = nn.BatchNorm3d(affine), "none"; get_act "relu" | "leakyrelu" | "elu" through
@@ -243,7 +266,9 @@ int b21_conv3d_wgrad_march(const void* x, int ldx, const void* dz, int lddz, flo
  * multiplied by the MONAI ResidualSELayer gate (b21_se_gate: se_scale, from the channel means se_mean) and dy is the
  * gradient of that product; the gate's MLP gradients are accumulated into d_w1/d_b1/d_w2/d_b2.  dgamma/dbeta are
  * accumulated; colsum (optional, fp32 [c]) accumulates sum_v dz (= bias gradient of the producing conv).
- * workspace: n*c*48 bytes.  dz may alias dy. */
+ * workspace: b21_norm_bwd_workspace_bytes(n, c) bytes, 16-byte aligned (reduction tables spread over 32 / 16 copies so
+ * that the ~1200 blocks of a pass do not serialise on a few L2 atomic addresses).  dz may alias dy. */
+long long b21_norm_bwd_workspace_bytes(int n, int c);
 int b21_norm_bwd(const void* dy, int lddy, const void* z, int ldz, void* dz, int lddz, const double* stats,
                  const float* gamma, const float* beta, float* dgamma, float* dbeta, float* colsum,
                  const float* se_scale, const float* se_mean, const float* se_w1, const float* se_b1,
@@ -260,10 +285,12 @@ int b21_pool_bwd(const void* y, int ldy, const void* dpool, int ldp, const void*
 int b21_upsample2x_bwd(const void* dy, int lddy, void* dx, int lddx, int n, int d, int h, int w, int c, void* stream);
 int b21_upsample_f32_bwd(const float* dy, float* dx, int planes, int d, int h, int w, int s, void* stream);
 
-/* Backward of b21_head_conv: dx (bf16, += if accumulate) = scale * W^T dl; dws[n][k][c] += sum_v dl x (so that
- * dW = scale * dws and dscale = sum_k W dws); db[k] += sum_v dl. */
+/* Backward of b21_head_conv: dx (bf16, += if accumulate) = scale * W^T dl; dws[slot][n][k][c] += sum_v dl x (so that
+ * dW = scale * dws and dscale = sum_k W dws); db[slot][k] += sum_v dl.  Block b adds to copy b % slots of both tables
+ * (the caller zeroes them and sums the copies): one copy makes ~1200 blocks serialise on k*c L2 atomic addresses. */
 int b21_head_conv_bwd(const void* x, int ldx, const float* scale, const float* w, const float* dl, void* dx, int lddx,
-                      int accumulate, float* dws, float* db, int n, long long nvox, int c, int k, void* stream);
+                      int accumulate, float* dws, float* db, int slots, int n, long long nvox, int c, int k,
+                      void* stream);
 
 /* dst += src on ndhwc bf16 (gradient fan-in). */
 int b21_add_inplace(void* dst, int ldd, const void* src, int lds, long long nvox_total, int c, void* stream);
