@@ -83,6 +83,20 @@ class GradStore:
             fn()
         self._side_dirty = True
 
+    def side_fence(self):
+        """Event after the work enqueued on the side stream so far (None when nothing is pending there)."""
+        if not self._side_dirty:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return ev
+
+    def join_side(self):
+        """The current stream waits for everything enqueued on the side stream."""
+        if self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_dirty = False
+
     def _side_event(self):
         if not self._side_dirty:
             return ()
@@ -202,22 +216,37 @@ def _v2_forward_train(net, x8: torch.Tensor, want_deep: bool):
     convevo("bridge2", y2, cat2[..., :f[1] // 2], 2, f[1] // 2)
     convevo("bridge3", y3, cat3[..., :f[2] // 2], 4, f[2] // 2)
 
+    # Deep-supervision heads (1x1 conv to 3 classes + fp32 trilinear x4 / x2): HBM-bound launches that only the loss
+    # needs.  They run on the side stream under the tensor-bound decoder convs; outputs are allocated on the current
+    # stream, which waits for the side stream before the forward returns.
+    gs = net.grad_store()
+    deep_on = want_deep and net.deep_supervision
+    deeps: List[torch.Tensor] = []
+
+    def deep_head(name, src, scale):
+        nk, (sd, sh, sw) = net.num_classes, src.shape[1:4]
+        low = torch.empty((n, nk, sd, sh, sw), dtype=torch.float32, device=src.device)
+        up = torch.empty((n, nk, sd * scale, sh * scale, sw * scale), dtype=torch.float32, device=src.device)
+        gs.on_side(lambda: ops.upsample_f32(ops.head_conv(src, pk[name + ".w"], pk[name + ".bias"], out=low), scale, out=up))
+        deeps.append(up)
+
     u = convevo("upconv3", assp, B("uc3", 8, f[3] // 4), 8, f[3] // 4)
     ops.upsample2x(u, cat3[..., f[2] // 2:])
     yd3, s = block("decoder3", cat3, 4, f[2])
     ops.scale_pool(yd3, s, full=yd3, mode=0)
+    if deep_on:
+        deep_head("deep3.0", yd3, 4)
     u = convevo("upconv2", yd3, B("uc2", 4, f[2] // 4), 4, f[2] // 4)
     ops.upsample2x(u, cat2[..., f[1] // 2:])
     yd2, s = block("decoder2", cat2, 2, f[1])
     ops.scale_pool(yd2, s, full=yd2, mode=0)
+    if deep_on:
+        deep_head("deep2.0", yd2, 2)
     u = convevo("upconv1", yd2, B("uc1", 2, f[1] // 4), 2, f[1] // 4)
     ops.upsample2x(u, cat1[..., f[0] // 2:])
     a1, s1 = block("decoder1", cat1, 1, f[0])
     out = ops.head_conv(a1, pk["out_conv.w"], pk["out_conv.bias"], scale=s1)
-    deeps: List[torch.Tensor] = []
-    if want_deep and net.deep_supervision:
-        deeps.append(ops.upsample_f32(ops.head_conv(yd3, pk["deep3.0.w"], pk["deep3.0.bias"]), 4))
-        deeps.append(ops.upsample_f32(ops.head_conv(yd2, pk["deep2.0.w"], pk["deep2.0.bias"]), 2))
+    gs.join_side()
     tape["__meta__"] = dict(shape=(n, d, h, w), ws=ws, y=(y1, y2, y3, y4), yd=(yd3, yd2, a1), s1=s1, acat=acat, assp=assp,
                             cats=(cat1, cat2, cat3), want_deep=bool(deeps))
     return out, deeps, tape
@@ -285,17 +314,19 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
     if meta["want_deep"]:
         dl3 = ddeeps[0] if ddeeps[0] is not None else None
         dl2 = ddeeps[1] if ddeeps[1] is not None else None
+        # the adjoints of the deep heads are first needed at decoder2 / decoder3: side stream, under decoder1's backward
         if dl3 is not None:
-            head_bwd("deep3.0", yd3, ops.upsample_f32_bwd(dl3.float(), 4), g_yd3)
+            gs.on_side(lambda: head_bwd("deep3.0", yd3, ops.upsample_f32_bwd(dl3.float(), 4), g_yd3))
         else:
             g_yd3.zero_()
         if dl2 is not None:
-            head_bwd("deep2.0", yd2, ops.upsample_f32_bwd(dl2.float(), 2), g_yd2)
+            gs.on_side(lambda: head_bwd("deep2.0", yd2, ops.upsample_f32_bwd(dl2.float(), 2), g_yd2))
         else:
             g_yd2.zero_()
     else:
         g_yd3.zero_()
         g_yd2.zero_()
+    deep_fence = gs.side_fence()
     if dout is None:
         dout = torch.zeros((n, net.num_classes, d, h, w), dtype=torch.float32, device=a1.device)
     head_bwd("out_conv", a1, dout.float(), g_a1, scale_fold=meta["s1"])
@@ -306,6 +337,8 @@ def _backward_v2(net, tape, dout: Optional[torch.Tensor], ddeeps: List[Optional[
     g_uc1, tmp2 = B("uc1", 2, f[1] // 4), B("tmp2", 2, f[1])
     ops.upsample2x_bwd(g_cat1[..., f[0] // 2:], g_uc1)
     convevo_bwd("upconv1", g_uc1, g_uc1, tmp2)
+    if deep_fence is not None:
+        torch.cuda.current_stream().wait_event(deep_fence)  # g_yd2 / g_yd3 hold the deep heads' gradients from here on
     ops.add_inplace(g_yd2, tmp2)
     g_b1, g_y1 = B("b1", 1, f[0] // 2), B("y1", 1, f[0])
     convevo_bwd("bridge1", g_cat1[..., :f[0] // 2], g_b1, g_y1)

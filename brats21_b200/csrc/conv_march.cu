@@ -619,15 +619,11 @@ extern "C" int b21_pack_conv_weight_march_fold(const float* w, void* packed, int
   B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_march_fold: bad args");
   B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_march_fold: the bias table needs ws and B");
   B21_CHECK_ARG(cout % 8 == 0, "pack_conv_weight_march_fold: output channels %d must be a multiple of 8", cout);
-  const int kc = march_kc(cin);
-  const size_t total = march_wbytes(cin, cout) / 2;
-  const int threads = 256;
-  const int bx = int((total + threads - 1) / threads) < 512 ? int((total + threads - 1) / threads) : 512;
+  b21_pack_job job;  // source-tiled packing (pack.cuh); padding is not written: the caller zero-fills the buffer once
+  int r = b21_pack_job_march(w, packed, cout, cin, 0, &job);
+  if (r) return r;
   BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, 27};
-  pack_march_weight_kernel<<<dim3(bx + (table ? 27 : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, kc, 0, scale, ldscale, bx, tab);
-  B21_LAUNCH_CHECK("pack_march_weight_kernel(fold)");
-  return B21_OK;
+  return launch_pack_fold_tile(reinterpret_cast<const PackJob&>(job), scale, ldscale, nsamples, tab, (cudaStream_t)stream);
 }
 
 template <int COUT, int NG, int KS>

@@ -595,16 +595,11 @@ extern "C" int b21_pack_conv_weight_slide_fold(const float* w, void* packed, int
                                                const float* b_in, float* table, void* stream) {
   B21_CHECK_ARG(w && packed && scale && nsamples > 0 && ldscale >= cin, "pack_conv_weight_slide_fold: bad args");
   B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_slide_fold: the bias table needs ws and B");
-  SlideCfg c;
-  B21_CHECK_ARG(slide_config(cin, cout, &c), "pack_conv_weight_slide_fold: (cin %d, cout %d) unsupported", cin, cout);
-  const size_t total = size_t(27) * c.nchunks * c.kc * cout * 8;
-  const int threads = 256;
-  const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
+  b21_pack_job job;  // source-tiled packing (pack.cuh); padding is not written: the caller zero-fills the buffer once
+  int r = b21_pack_job_slide(w, packed, cout, cin, 0, &job);
+  if (r) return r;
   BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, 27};
-  pack_slide_weight_kernel<<<dim3(bx + (table ? 27 : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, cout, c.kc, c.nt, 0, scale, ldscale, bx, tab, c.nchunks);
-  B21_LAUNCH_CHECK("pack_slide_weight_kernel(fold)");
-  return B21_OK;
+  return launch_pack_fold_tile(reinterpret_cast<const PackJob&>(job), scale, ldscale, nsamples, tab, (cudaStream_t)stream);
 }
 
 static int slide_fwd_impl(const void* x, int ldx, const void* w_slide, const float* bias, void* y, int ldy,

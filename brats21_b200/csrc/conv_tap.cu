@@ -276,17 +276,14 @@ extern "C" int b21_pack_conv_weight_fold(const float* w, void* packed, int cout,
   B21_CHECK_ARG(!table || (ws && b_in), "pack_conv_weight_fold: the bias table needs ws and B");
   B21_CHECK_ARG(k == 1 || k == 3, "pack_conv_weight_fold: k must be 1 or 3 (got %d)", k);
   B21_CHECK_ARG(cin_padded >= cin && cin_padded % 8 == 0, "pack_conv_weight_fold: bad inner padding");
-  const int T = k * k * k;
-  const int rows_padded = b21_conv_cout_padded(cout);
-  const size_t total = size_t(T) * rows_padded * cin_padded;
-  const int threads = 256;
-  const int bx = int((total + threads - 1) / threads) < 1024 ? int((total + threads - 1) / threads) : 1024;
-  const int ncls = T == 27 ? 27 : 1;
+  // source-tiled packing (pack.cuh): the fp32 weight is read in coalesced 16 x 16 x taps tiles, once per sample; padding
+  // rows / channels of the images are not written (the caller zero-fills the buffer once)
+  const int ncls = k == 3 ? 27 : 1;
+  b21_pack_job job;
+  int r = b21_pack_job_tap(w, packed, cout, cin, cin_padded, k, 0, &job);
+  if (r) return r;
   BiasTableArgs tab = {ws, bias, b_in, table, ldscale, cout, cin, ncls};
-  pack_conv_weight_kernel<<<dim3(bx + (table ? ncls : 0), nsamples), threads, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, rows_padded, cin_padded, T, 0, scale, ldscale, bx, tab);
-  B21_LAUNCH_CHECK("pack_conv_weight_kernel(fold)");
-  return B21_OK;
+  return launch_pack_fold_tile(reinterpret_cast<const PackJob&>(job), scale, ldscale, nsamples, tab, (cudaStream_t)stream);
 }
 
 extern "C" int b21_conv3d_fwd(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,

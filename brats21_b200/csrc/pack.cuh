@@ -4,6 +4,7 @@
 // conv_slide.cu call the same element functions, so both routes produce identical images.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_runtime.h>
 #include <stddef.h>
 
 namespace b21 {
@@ -95,5 +96,68 @@ __device__ __forceinline__ size_t pack_slide_index(int ro, int ki, int tap, int 
   const int ng = nt / 8, tile = ro / nt, rem = ro - tile * nt, q = ki >> 3, chunk = q / kc, c = q - chunk * kc;
   return (((((size_t(tile) * nchunks + chunk) * 27 + tap) * kc + c) * ng + (rem >> 3)) * 8 + (rem & 7)) * 8 + (ki & 7);
 }
+
+constexpr int kPT = 16;                // source tile: 16 output channels x 16 input channels x all taps
+constexpr int kPitch = kPT * 27 + 1;   // odd row pitch of the shared tile: the transposed walk stays (almost) conflict-free
+
+// One block (256 threads) re-packs source tile `t` of the group jobs[first..last] (same source weight): it reads the
+// tile's nco x (nci * taps) contiguous floats once into `tile` (kPT * kPitch floats of shared memory) and writes every
+// image of the group in runs of 16 consecutive bf16.  scale != NULL multiplies input channel ci by scale[ci]
+// (per-sample folded weights; forward images only).  Padding rows / channels of the images are not touched.
+__device__ __forceinline__ void pack_tile_block(const PackJob* jobs, int first, int last, int t,
+                                                const float* __restrict__ scale, float* tile) {
+  const PackJob& j0 = jobs[first];
+  const int cout = j0.cout, cin = j0.cin;
+  const int T = j0.kind == kPackTap ? j0.p2 : 27;
+  const int cin_tiles = (cin + kPT - 1) / kPT;
+  const int co0 = (t / cin_tiles) * kPT, ci0 = (t % cin_tiles) * kPT;
+  const int nco = cout - co0 < kPT ? cout - co0 : kPT, nci = cin - ci0 < kPT ? cin - ci0 : kPT;
+  // source rows: w[co][ci0 .. ci0 + nci)[0 .. T) is one contiguous run of nci * T floats; a warp per row
+  const int run = nci * T, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < nco; r += 8) {
+    const float* src = j0.w + (size_t(co0 + r) * cin + ci0) * T;
+    for (int k = lane; k < run; k += 32) tile[r * kPitch + k] = src[k];
+  }
+  __syncthreads();
+  // thread (a, b) = image (row, inner channel) within the tile, b fastest: 16 consecutive bf16 per run; it walks the
+  // taps with a constant destination stride (every image layout is linear in the tap index for a fixed element)
+  const int a = threadIdx.x >> 4, b = threadIdx.x & 15;
+  for (int q = first; q <= last; ++q) {
+    const PackJob& j = jobs[q];
+    const int na = j.tf ? nci : nco, nb = j.tf ? nco : nci;
+    if (a >= na || b >= nb) continue;
+    const int col = j.tf ? b : a, cil = j.tf ? a : b;  // source (co, ci) within the tile
+    const float* src = tile + col * kPitch + cil * T;
+    const int r = (j.tf ? ci0 : co0) + a, ki = (j.tf ? co0 : ci0) + b;
+    const float sc = scale ? scale[ci0 + cil] : 1.f;
+    if (j.kind == kPackTap) {
+      const size_t step = size_t(j.p0) * j.p1;
+      size_t dst = pack_tap_index(r, ki, 0, j.p0, j.p1);
+      for (int tap = 0; tap < T; ++tap, dst += step) j.out[dst] = __float2bfloat16_rn(src[j.tf ? T - 1 - tap : tap] * sc);
+    } else if (j.kind == kPackMarch) {
+      // index(kd, kh, kw) = index(0, 0, 0) + (kh * 3 + kw) * s9 - kd * sd
+      const size_t i0 = pack_march_index(r, ki, 0, 0, 0, j.p0, j.p1);
+      const size_t s9 = pack_march_index(r, ki, 0, 0, 1, j.p0, j.p1) - i0, sd = i0 - pack_march_index(r, ki, 1, 0, 0, j.p0, j.p1);
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int tap = kd * 9 + t9;
+          j.out[i0 + t9 * s9 - kd * sd] = __float2bfloat16_rn(src[j.tf ? 26 - tap : tap] * sc);
+        }
+    } else {
+      const size_t i0 = pack_slide_index(r, ki, 0, j.p1, j.p2, j.p3);
+      const size_t st = pack_slide_index(r, ki, 1, j.p1, j.p2, j.p3) - i0;
+#pragma unroll
+      for (int tap = 0; tap < 27; ++tap) j.out[i0 + tap * st] = __float2bfloat16_rn(src[j.tf ? 26 - tap : tap] * sc);
+    }
+  }
+}
+
+struct BiasTableArgs;
+// Per-sample folded packing (conv_tap.cu / conv_march.cu / conv_slide.cu): image s = pack(w * scale[s][ci]) at
+// out + s * job.total, plus the bias-table rows when tab.table != NULL; one launch (pack_batch.cu).
+int launch_pack_fold_tile(const PackJob& job, const float* scale, int ldscale, int nsamples, const BiasTableArgs& tab,
+                          cudaStream_t stream);
 
 }  // namespace b21

@@ -97,15 +97,22 @@ _COUNT_CACHE_ENTRIES = 8
 _count_cache: "collections.OrderedDict[Tuple, torch.Tensor]" = collections.OrderedDict()
 
 
+_floor_cache: Dict[Tuple, float] = {}
+
+
 def importance_floor(profiles) -> float:
     """MONAI clamps the 3-D importance map at its smallest non-zero value (compute_importance_map).  The map is the
     outer product of the profiles, so that value is the product of the per-axis smallest non-zero entries, and the clamp
     only changes entries where some factor is exactly 0 — possible only when the 4-sigma truncation falls inside the
     window (sigma_scale < 1/8).  Returns 0.0 (no clamp needed) when every profile is strictly positive."""
-    if all(bool((p > 0).all()) for p in profiles):
-        return 0.0
-    mins = [p[p > 0].min() for p in profiles]
-    return float((mins[0] * mins[1]) * mins[2])
+    key = tuple((p.data_ptr(), p.numel()) for p in profiles)  # the profiles are cached tensors: one host sync per geometry,
+    if key not in _floor_cache:                                # not three per TTA variant (24 pipeline drains per volume)
+        if all(bool((p > 0).all()) for p in profiles):
+            _floor_cache[key] = 0.0
+        else:
+            mins = [p[p > 0].min() for p in profiles]
+            _floor_cache[key] = float((mins[0] * mins[1]) * mins[2])
+    return _floor_cache[key]
 
 
 def count_map(image_size, roi, overlap, mode, sigma_scale, device) -> torch.Tensor:

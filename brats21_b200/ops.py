@@ -200,7 +200,8 @@ def _fold_prepare(pw: "PackedConv", a_in, b_in):
             nbytes = pw.w_march.numel() * 2
         else:
             nbytes = pw.w_slide.numel() * 2
-        f[key] = (torch.empty((n, nbytes // 2), dtype=torch.bfloat16, device=dev),
+        # zero-filled once: the per-sample packing rewrites the valid elements only (padding rows / channels stay 0)
+        f[key] = (torch.zeros((n, nbytes // 2), dtype=torch.bfloat16, device=dev),
                   torch.empty((n, ncls, pw.cout), dtype=torch.float32, device=dev))
     packed, table = f[key]
     ld = a_in.stride(0)
@@ -386,10 +387,12 @@ def upsample2x(x, out):
     return out
 
 
-def upsample_f32(x, s):
+def upsample_f32(x, s, out=None):
     """[N, K, d, h, w] fp32 -> [N, K, s*d, s*h, s*w] (trilinear, align_corners=True)."""
     n, k, d, h, w = x.shape
-    out = torch.empty((n, k, s * d, s * h, s * w), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((n, k, s * d, s * h, s * w), dtype=torch.float32, device=x.device)
+    assert out.shape == (n, k, s * d, s * h, s * w) and out.dtype == torch.float32 and out.is_contiguous()
     call("b21_upsample_f32", ptr(x.contiguous()), ptr(out), n * k, d, h, w, s, stream_ptr())
     return out
 

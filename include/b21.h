@@ -126,7 +126,9 @@ int b21_border_weight_sums(const float* w, float* ws, int cout, int cin, int tap
 int b21_bias_table(const float* ws, const float* bias, const float* b_in, int ldab, float* table, int n, int cout,
                    int cin, int ncls, void* stream);
 /* The per-sample packing kernels also emit the bias table in the same launch when `table` != NULL
- * (ws / bias / b_in as for b21_bias_table; B rows share `ldscale`). */
+ * (ws / bias / b_in as for b21_bias_table; B rows share `ldscale`).  They read the fp32 weight in coalesced
+ * 16 x 16 x taps tiles and rewrite the VALID elements of every per-sample image only: the caller zero-fills `packed`
+ * once (padding rows / channels must be 0). */
 int b21_pack_conv_weight_fold(const float* w, void* packed, int cout, int cin, int cin_padded, int k,
                               const float* scale, int ldscale, int nsamples, const float* ws, const float* bias,
                               const float* b_in, float* table, void* stream);
