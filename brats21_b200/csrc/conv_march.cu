@@ -95,7 +95,7 @@ __device__ __forceinline__ MarchItem decode_item(const ConvMarchParams& p, int i
 // scout -> issuer message: everything the issuing thread needs for one input plane (48 bytes, three 16-byte words)
 struct PlaneMsg {
   uint32_t a_lo, a_hi, b_lo, b_hi;   // A / B shared-memory descriptors of the plane's first tap / k-step
-  uint32_t col0, id0, id1, b1;       // accumulator column, instruction descriptors, B offset of the wrapped groups
+  uint32_t col0, id0, id1, b1;       // accumulator column, instruction descriptor (id1 / b1: unused since the ring no longer wraps)
   uint32_t stage, accf_lo, accf_hi, pad;  // plane stage to release, ring slots to commit (0xffffffff = none / end)
 };
 constexpr int kMsgRing = 8;
@@ -110,7 +110,14 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   const ConvMarchParams p) {
   constexpr int kMThreads = kMThreadsBase + NG * 128 + 32;  // + the scout warp
   constexpr int PC = NG > 2 ? 16 : COUT;  // columns per epilogue pass
-  constexpr uint32_t RING = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;  // accumulator slots in TMEM
+  // Accumulator slots in TMEM: RING logical slots + 2 OVERFLOW slots.  The three column groups of a plane are adjacent
+  // slots r_lo .. r_lo + 2; a plain ring wraps for 2 of every RING planes and needs two MMAs (N = 96 and 48: 56 + 45
+  // cycles instead of 72 for one N = 144 MMA).  With the physical slots RING and RING + 1 standing in for logical
+  // slots 0 and 1 whenever a window starts at RING - 2 or RING - 1, every plane is ONE contiguous MMA; the epilogue
+  // sums (and re-zeroes) both physical copies of logical slots 0 and 1.  Barriers are per LOGICAL slot.
+  constexpr uint32_t PHYS = (512 / COUT) < kMMaxRing ? (512 / COUT) : kMMaxRing;
+  constexpr uint32_t RING = PHYS - 2;
+  static_assert(RING >= 4, "accumulator ring too short");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMMaxStages];
@@ -274,17 +281,15 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               }
             }
             mbar_wait_a(full0 + 8u * stage, phase);
-            const int room = int(RING - r_lo);
-            const int len0 = ngroups < room ? ngroups : room, len1 = ngroups - len0;  // at most one ring wrap
             PlaneMsg m;
             const uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
             const uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
             m.a_lo = uint32_t(a_row); m.a_hi = uint32_t(a_row >> 32);
             m.b_lo = uint32_t(bq); m.b_hi = uint32_t(bq >> 32);
-            m.col0 = tmem_base + r_lo * COUT;
-            m.id0 = len0 == 3 ? idesc3 : (len0 == 2 ? idesc2 : idesc1);
-            m.id1 = len1 == 2 ? idesc2 : idesc1;
-            m.b1 = len1 ? uint32_t(len0) * COUT : 0u;  // 0: no ring wrap (a single MMA per tap and k-step)
+            m.col0 = tmem_base + r_lo * COUT;  // physical slots r_lo .. r_lo + ngroups - 1 <= RING + 1: never wraps
+            m.id0 = ngroups == 3 ? idesc3 : (ngroups == 2 ? idesc2 : idesc1);
+            m.id1 = 0;
+            m.b1 = 0;
             m.stage = uint32_t(stage);
             m.accf_lo = i >= 2 ? r_lo : kEnd;  // output plane so = i - 1 is complete after this plane
             m.accf_hi = kEnd;
@@ -336,33 +341,15 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint64_t a_row = (uint64_t(m.a_hi) << 32) | m.a_lo, bq0 = (uint64_t(m.b_hi) << 32) | m.b_lo;
           if constexpr (KS > 0) {
             constexpr uint64_t kAStep = 2u * (uint64_t(kMChunkBytes) >> 4), kBStep = 2u * (uint64_t((3 * COUT / 8) * 128) >> 4);
-            if (m.b1 == 0) {  // common case: one MMA per (tap, k-step), N = ngroups * COUT
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                if (kh < nkh) {
+            for (int kh = 0; kh < 3; ++kh) {  // one MMA per (tap, k-step), N = ngroups * COUT
+              if (kh < nkh) {
 #pragma unroll
-                  for (int kw = 0; kw < 3; ++kw) {
+                for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-                      umma_bf16(m.col0, a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep,
-                                bq0 + uint64_t((kh * 3 + kw) * KS + ks) * kBStep, m.id0, 1u);
-                  }
-                }
-              }
-            } else {
-#pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                if (kh < nkh) {
-#pragma unroll
-                  for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                      const uint64_t ad = a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep;
-                      const uint64_t bd = bq0 + uint64_t((kh * 3 + kw) * KS + ks) * kBStep;
-                      umma_bf16(m.col0, ad, bd, m.id0, 1u);
-                      umma_bf16(tmem_base, ad, bd + m.b1, m.id1, 1u);
-                    }
-                  }
+                  for (int ks = 0; ks < KS; ++ks)
+                    umma_bf16(m.col0, a_row + uint64_t(kh * kMHW + kw) + uint64_t(ks) * kAStep,
+                              bq0 + uint64_t((kh * 3 + kw) * KS + ks) * kBStep, m.id0, 1u);
                 }
               }
             }
@@ -374,7 +361,6 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 uint64_t ad = a_tap;
                 for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bq += b_step) {
                   umma_bf16(m.col0, ad, bq, m.id0, 1u);
-                  if (m.b1 != 0) umma_bf16(tmem_base, ad, bq + m.b1, m.id1, 1u);
                 }
               }
             }
@@ -396,7 +382,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     constexpr int GS = COUT / 8;  // channels per norm group
     // accumulators start at zero and are re-zeroed after every drain: the MMAs always accumulate
     if (grp == 0) {
-      for (uint32_t c0 = 0; c0 < RING * COUT; c0 += 16) tmem_st16_zero(tlane + c0);
+      for (uint32_t c0 = 0; c0 < PHYS * COUT; c0 += 16) tmem_st16_zero(tlane + c0);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -431,6 +417,8 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         use_par ^= 1u << r;
         tc_fence_after();
         const uint32_t tcol = tlane + r * COUT;
+        const bool aliased = r < 2;  // logical slots 0 and 1 have a second physical copy (slots RING, RING + 1)
+        const uint32_t tcol2 = tcol + RING * COUT;
         const uint32_t acce_r = acce0 + 8u * r;
         r = r + 1 == RING ? 0 : r + 1;
         const float* tb = (trow && valid) ? trow + size_t(border_class(it.d0 + so, p.D)) * 9 * COUT : nullptr;
@@ -444,6 +432,17 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < PC; c += 16) tmem_st16_zero(tcol + uint32_t(c0 + c));
+            if (aliased) {
+#pragma unroll
+              for (int c = 0; c < PC; c += 16) {
+                float t[16];
+                tmem_ld16(tcol2 + uint32_t(c0 + c), t);
+                tmem_ld_wait();
+                tmem_st16_zero(tcol2 + uint32_t(c0 + c));
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[c + q] += t[q];
+              }
+            }
           } else {
 #pragma unroll
             for (int c = 0; c < PC; ++c) v[c] = 0.f;
