@@ -26,6 +26,11 @@ _SIGNATURES = {
     "b21_pack_job_march": [_vp, _vp, _i, _i, _i, _vp],
     "b21_pack_job_slide": [_vp, _vp, _i, _i, _i, _vp],
     "b21_pack_batch": [_vp, _i, _i, _vp],
+    "b21_conv_input_supported": [_i, _i],
+    "b21_conv_input_weight_bytes": [_i],
+    "b21_pack_conv_weight_input": [_vp, _vp, _i, _i, _vp],
+    "b21_pack_job_input": [_vp, _vp, _i, _i, _vp],
+    "b21_conv3d_input_fwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "b21_conv_march_supported": [_i, _i],
     "b21_conv_march_weight_bytes": [_i, _i],
     "b21_pack_conv_weight_march": [_vp, _vp, _i, _i, _i, _vp],
@@ -125,6 +130,7 @@ def load():
         fn.restype = _i
     lib.b21_conv_march_weight_bytes.restype = C.c_longlong
     lib.b21_conv_slide_weight_bytes.restype = C.c_longlong
+    lib.b21_conv_input_weight_bytes.restype = C.c_longlong
     lib.b21_keep_components_workspace_bytes.restype = C.c_longlong
     lib.b21_norm_bwd_workspace_bytes.restype = C.c_longlong
     lib.b21_replace_rare_workspace_bytes.restype = C.c_longlong
@@ -153,7 +159,8 @@ def stream_ptr():
 _LAUNCHES = {"b21_conv_cout_padded": 0, "b21_conv_point_supported": 0, "b21_conv_march_supported": 0,
              "b21_conv_march_weight_bytes": 0, "b21_conv_slide_supported": 0, "b21_conv_wgrad_march_supported": 0, "b21_conv_slide_weight_bytes": 0, "b21_conv3d_fwd": 1, "b21_norm_bwd": 3, "b21_dice_fwd": 2, "b21_ce_fwd": 2,
              "b21_keep_components_workspace_bytes": 0, "b21_norm_bwd_workspace_bytes": 0, "b21_pack_job_tap": 0,
-             "b21_pack_job_march": 0, "b21_pack_job_slide": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
+             "b21_pack_job_march": 0, "b21_pack_job_slide": 0, "b21_pack_job_input": 0, "b21_conv_input_supported": 0,
+             "b21_conv_input_weight_bytes": 0, "b21_replace_rare_workspace_bytes": 0, "b21_foreground_bbox": 2,
              "b21_keep_components": 4, "b21_replace_rare_labels": 5}
 launch_count = 0
 

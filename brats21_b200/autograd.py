@@ -225,9 +225,18 @@ def _v2_forward_train(net, x8: torch.Tensor, want_deep: bool):
 
     def deep_head(name, src, scale):
         nk, (sd, sh, sw) = net.num_classes, src.shape[1:4]
-        low = torch.empty((n, nk, sd, sh, sw), dtype=torch.float32, device=src.device)
         up = torch.empty((n, nk, sd * scale, sh * scale, sw * scale), dtype=torch.float32, device=src.device)
-        gs.on_side(lambda: ops.upsample_f32(ops.head_conv(src, pk[name + ".w"], pk[name + ".bias"], out=low), scale, out=up))
+
+        def run():
+            # The low-resolution logits are a temporary of the SIDE stream and must be allocated under it: a block taken
+            # from the current stream's pool goes back to that pool as soon as the last reference dies — while the side
+            # stream may still be reading it — and the next small allocation of the main stream (SE gate, channel means)
+            # lands on top of it.  (Seen as a deep-supervision loss that was off by 0.1 % in about half of the runs of the
+            # two-process data-parallel test, profiles/r02z_grad_noise.md.)
+            low = torch.empty((n, nk, sd, sh, sw), dtype=torch.float32, device=src.device)
+            ops.upsample_f32(ops.head_conv(src, pk[name + ".w"], pk[name + ".bias"], out=low), scale, out=up)
+
+        gs.on_side(run)
         deeps.append(up)
 
     u = convevo("upconv3", assp, B("uc3", 8, f[3] // 4), 8, f[3] // 4)

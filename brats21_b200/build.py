@@ -24,6 +24,15 @@ NVCC_FLAGS = [
 ]
 
 
+# B21_NVCC_EXTRA: extra nvcc flags (e.g. -DB21_WAIT_HINT_NS=0 for an A/B build); B21_BUILD_OUT: library path of that build
+import shlex  # noqa: E402
+
+NVCC_FLAGS += shlex.split(os.environ.get("B21_NVCC_EXTRA", ""))
+if os.environ.get("B21_BUILD_OUT"):
+    LIB_PATH = Path(os.environ["B21_BUILD_OUT"]).resolve()
+    STAMP = LIB_PATH.with_suffix(".stamp")
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
@@ -51,7 +60,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB_PATH
     objs = []
-    build_dir = PKG_DIR / "build"
+    build_dir = PKG_DIR / ("build" if not os.environ.get("B21_BUILD_OUT") else "build_" + LIB_PATH.stem)
     build_dir.mkdir(exist_ok=True)
     procs = []
     for src in _sources():

@@ -186,7 +186,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // every plane stage released <=> every MMA that read the old weights has completed
             for (int k = 0; k < p.stages; ++k) {
               const int s2 = stage + k < p.stages ? stage + k : stage + k - p.stages;
-              mbar_wait_a(empty0 + 8u * s2, (stage + k < p.stages ? phase : phase ^ 1) ^ 1);
+              mbar_wait_sleep_a(empty0 + 8u * s2, (stage + k < p.stages ? phase : phase ^ 1) ^ 1);
             }
           }
           w_n = it.n;
@@ -200,7 +200,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int i = 0; i <= it.Lc + 1; ++i) {
           const int dz = it.d0 - 1 + i;
           if (dz < 0 || dz >= p.D) continue;
-          mbar_wait_a(empty0 + 8u * stage, phase ^ 1);
+          mbar_wait_sleep_a(empty0 + 8u * stage, phase ^ 1);
           const uint32_t fb = full0 + 8u * stage;
           if (p.variant & 4) {  // debug: no loads
             mbar_arrive_a(fb);
@@ -255,7 +255,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const MarchItem it = decode_item(p, item);
           if (w_n < 0 || (p.ex.wstride != 0 && it.n != w_n)) {
             w_n = it.n;
-            mbar_wait(&w_bar, w_par);
+            mbar_wait_spin(&w_bar, w_par);
             w_par ^= 1u;
           }
           uint32_t r_lo = r_base;
@@ -275,12 +275,12 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               if (g < ngroups && sg >= next_fresh) {  // first contribution: wait until the slot is drained and zeroed
                 uint32_t r = r_lo + uint32_t(g);
                 r = r >= RING ? r - RING : r;
-                mbar_wait_a(acce0 + 8u * r, (claim_par >> r) & 1u);
+                mbar_wait_spin_a(acce0 + 8u * r, (claim_par >> r) & 1u);
                 claim_par ^= 1u << r;
                 next_fresh = sg + 1;
               }
             }
-            mbar_wait_a(full0 + 8u * stage, phase);
+            mbar_wait_spin_a(full0 + 8u * stage, phase);
             PlaneMsg m;
             const uint64_t a_row = dA + uint64_t((p_addr + uint32_t(stage) * plane_bytes) >> 4);
             const uint64_t bq = bd0 + uint64_t(jlo) * COUT;  // descriptor address field is in 16 B units
@@ -413,7 +413,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           r = r + 1 == RING ? 0 : r + 1;
           continue;
         }
-        mbar_wait_a(accf0 + 8u * r, (use_par >> r) & 1u);
+        mbar_wait_sleep_a(accf0 + 8u * r, (use_par >> r) & 1u);
         use_par ^= 1u << r;
         tc_fence_after();
         const uint32_t tcol = tlane + r * COUT;

@@ -101,7 +101,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (w_n >= 0) {  // every activation stage released <=> every MMA that read the old weights has completed
             for (int k = 0; k < p.stages; ++k) {
               const int s2 = s + k < p.stages ? s + k : s + k - p.stages;
-              mbar_wait(&empty_bar[s2], (s + k < p.stages ? ph : ph ^ 1) ^ 1);
+              mbar_wait_sleep(&empty_bar[s2], (s + k < p.stages ? ph : ph ^ 1) ^ 1);
             }
           }
           w_n = n;
@@ -110,7 +110,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_3d(sB + size_t(ck) * BN * 128, &tmB, &w_bar, ck * 64, 0, p.ex.wstride != 0 ? n : 0);
         }
         for (int ck = 0; ck < p.chunks; ++ck) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_sleep(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], kPtABytes);
           tma_load_3d(sA + size_t(s) * kPtABytes, &tmA, &full_bar[s], ck * 64, r0, n);
           if (++s == p.stages) {
@@ -196,7 +196,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         cur_n = n;
       }
       const uint32_t buf = it & 1u;
-      mbar_wait(&accf_bar[buf], (it >> 1) & 1u);
+      mbar_wait_sleep(&accf_bar[buf], (it >> 1) & 1u);
       tc_fence_after();
       float v[BN];
 #pragma unroll

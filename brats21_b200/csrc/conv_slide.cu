@@ -145,7 +145,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           const int ch0 = p.nchunks > 1 ? (ps - g * p.nchunks) * p.kc * 8 : 0;
           for (int jj = 0; jj < NP; ++jj) {
             const int j = 3 * g + jj;
-            mbar_wait_a(pempty0 + 8u * slot, phase ^ 1);
+            mbar_wait_sleep_a(pempty0 + 8u * slot, phase ^ 1);
             const uint32_t fb = pfull0 + 8u * slot;
             if (j <= it.Lc + 1 && !(p.variant & 1)) {  // planes beyond the segment halo only feed skipped output planes
               const uint32_t dst = p_addr + uint32_t(slot) * plane_bytes;
@@ -179,7 +179,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
           const uint8_t* wt = wt0 + size_t(gc % p.nchunks) * 27 * p.tap_bytes;
           for (int tap = 0; tap < 27; ++tap) {  // tap = kd * 9 + kh * 3 + kw: phase kd walks taps kd*9 .. kd*9+8
             for (int sub = 0; sub < kWsub; ++sub) {
-              mbar_wait_a(wempty0 + 8u * ws, wph ^ 1);
+              mbar_wait_sleep_a(wempty0 + 8u * ws, wph ^ 1);
               const uint32_t nb = sub == 0 ? sub_bytes0 : sub_bytes1;
               const uint32_t fb = wfull0 + 8u * ws;
               if (p.variant & 2) {
@@ -364,7 +364,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
 #pragma unroll
       for (int b = 0; b < NCS; ++b) csum[b] = 0.f;
       for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
-        mbar_wait_a(accf0 + 8u * slot, par);
+        mbar_wait_sleep_a(accf0 + 8u * slot, par);
         tc_fence_after();
         float v[NT];
 #pragma unroll

@@ -85,7 +85,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int kb = 0; kb < numK; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait_sleep(&empty_bar[s], ph ^ 1);
         const int tap = kb / p.chunks, ck = kb - tap * p.chunks;
         int kd = 0, kh = 0, kw = 0;
         if (p.taps == 27) {
@@ -134,7 +134,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cbase = ntile * p.BN;
     __nv_bfloat16* yrow = p.y + vox * size_t(p.ldy) + cbase;
 
-    mbar_wait(&tmem_full_bar, 0);
+    mbar_wait_sleep(&tmem_full_bar, 0);
     tc_fence_after();
 
     float gs = 0.f, gq = 0.f;

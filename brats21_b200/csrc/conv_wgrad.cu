@@ -88,7 +88,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int dt = q % p.tilesD;
         const int n = q / p.tilesD;
         const int w0 = wt * tw, h0 = ht * th, d0 = dt * td;
-        mbar_wait_a(ze0 + 8u * zs, zph ^ 1);
+        mbar_wait_sleep_a(ze0 + 8u * zs, zph ^ 1);
         mbar_expect_tx_a(zf0 + 8u * zs, 2u * kWgChunk);
         for (int c = 0; c < 2; ++c)
           tma_load_5d_a(z_addr + uint32_t(zs * 2 + c) * kWgChunk, &tmZ, zf0 + 8u * zs, mt * 128 + c * 64, w0, h0, d0, n);
@@ -97,7 +97,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const int tap = tap0 + j;
           int kd = 0, kh = 0, kw = 0;
           if (p.taps == 27) { kd = tap / 9 - 1; kh = (tap / 3) % 3 - 1; kw = tap % 3 - 1; }
-          mbar_wait_a(xe0 + 8u * xs, xph ^ 1);
+          mbar_wait_sleep_a(xe0 + 8u * xs, xph ^ 1);
           mbar_expect_tx_a(xf0 + 8u * xs, xstage_bytes);
           for (int c = 0; c < p.nchunks; ++c)
             tma_load_5d_a(x_addr + uint32_t(xs) * xstage_bytes + uint32_t(c) * kWgChunk, &tmX, xf0 + 8u * xs,
@@ -136,7 +136,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (t_end > t_begin) {
       const int quad = warp & 3;
       const int co = mt * 128 + quad * 32 + lane;
-      mbar_wait(&acc_bar, 0);
+      mbar_wait_sleep(&acc_bar, 0);
       tc_fence_after();
       for (int j = 0; j < ntap; ++j) {
         const int tap = tap0 + j;

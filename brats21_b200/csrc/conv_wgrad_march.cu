@@ -157,7 +157,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         const WgItem it = wg_decode(p, item);
         // order of consumption: x planes j = 0, 1, 2 | dz 0 | x 3 | dz 1 | ...
         for (int j = 0; j < it.Lc + 2; ++j) {
-          mbar_wait_a(xe0 + 8u * xs, xph ^ 1);
+          mbar_wait_sleep_a(xe0 + 8u * xs, xph ^ 1);
           mbar_expect_tx_a(xf0 + 8u * xs, xtx);
           const uint32_t dst = x_addr + uint32_t(xs) * xplane_bytes;
           if (R > 1) {
@@ -171,7 +171,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (++xs == p.xslots) { xs = 0; xph ^= 1; }
           if (j >= 2) {
             const int so = j - 2;
-            mbar_wait_a(ze0 + 8u * zs, zph ^ 1);
+            mbar_wait_sleep_a(ze0 + 8u * zs, zph ^ 1);
             mbar_expect_tx_a(zf0 + 8u * zs, ztx);
             const uint32_t zd = z_addr + uint32_t(zs) * zstage_bytes;
             if (R > 1) {
@@ -272,7 +272,7 @@ conv_wgrad_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const int row = quad * 32 + lane;
       const int shift = p.pair && row >= p.Cout ? 1 : 0;  // rows [Cout, 2 Cout): the copy of dz shifted in w
       const int co = row - shift * p.Cout;
-      mbar_wait(&acc_bar, 0);
+      mbar_wait_sleep(&acc_bar, 0);
       tc_fence_after();
       for (int t = 0; t < ntap; ++t) {
         const WgSet st = wg_set(p, t9_begin + t);

@@ -9,7 +9,7 @@
 
 namespace b21 {
 
-enum { kPackTap = 0, kPackMarch = 1, kPackSlide = 2 };
+enum { kPackTap = 0, kPackMarch = 1, kPackSlide = 2, kPackInput = 3 };
 
 // mirrors `b21_pack_job` of include/b21.h (64 bytes)
 struct PackJob {
@@ -17,7 +17,7 @@ struct PackJob {
   __nv_bfloat16* out;   // packed image
   long long total;      // elements of the image
   int kind, cout, cin, tf;
-  int p0, p1, p2, p3;   // tap: rows_padded, inner_padded, taps | march: rows, kc | slide: rows, kc, nt, nchunks
+  int p0, p1, p2, p3;   // tap: rows_padded, inner_padded, taps | march: rows, kc | slide: rows, kc, nt, nchunks | input: cout
   int blk0, nblk;       // block range of the job's GROUP (consecutive jobs with the same source weight share one range:
                         // one block per 16 x 16 (cout, cin) source tile)
 };
@@ -83,6 +83,21 @@ __device__ __forceinline__ float pack_slide_value(const float* __restrict__ w, s
   return v;
 }
 
+// input-conv image [6 chunks][3 cout / 8][8 n][8 k], n = (2 - kd) * cout + co, k = (kh * 3 + kw) * 4 + c (conv_input.cu)
+__device__ __forceinline__ float pack_input_value(const float* __restrict__ w, size_t i, int cout, int cin_o) {
+  const int ng = 3 * cout / 8;
+  const int k8 = int(i & 7), n8 = int((i >> 3) & 7);
+  size_t t = i >> 6;
+  const int g = int(t % ng);
+  const int chunk = int(t / ng);
+  const int k = chunk * 8 + k8, tap9 = k >> 2, c = k & 3, n = g * 8 + n8, kd = 2 - n / cout, co = n % cout;
+  return (tap9 < 9 && c < cin_o) ? w[(size_t(co) * cin_o + c) * 27 + kd * 9 + tap9] : 0.f;
+}
+__device__ __forceinline__ size_t pack_input_index(int co, int ci, int tap, int cout) {
+  const int kd = tap / 9, k = (tap % 9) * 4 + ci, n = (2 - kd) * cout + co;
+  return ((size_t(k >> 3) * (3 * cout / 8) + (n >> 3)) * 8 + (n & 7)) * 8 + (k & 7);
+}
+
 // Inverse maps: destination index of source element (co, ci, tap) in each image (used by the batched re-pack, which
 // walks the SOURCE in coalesced tiles).  r / ki are the image's row / inner channel (swapped for transpose_flip).
 __device__ __forceinline__ size_t pack_tap_index(int r, int ki, int tap, int rows_padded, int inner_padded) {
@@ -145,6 +160,11 @@ __device__ __forceinline__ void pack_tile_block(const PackJob* jobs, int first, 
           const int tap = kd * 9 + t9;
           j.out[i0 + t9 * s9 - kd * sd] = __float2bfloat16_rn(src[j.tf ? 26 - tap : tap] * sc);
         }
+    } else if (j.kind == kPackInput) {
+      if (ki < 4) {
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) j.out[pack_input_index(r, ki, tap, j.p0)] = __float2bfloat16_rn(src[tap] * sc);
+      }
     } else {
       const size_t i0 = pack_slide_index(r, ki, 0, j.p1, j.p2, j.p3);
       const size_t st = pack_slide_index(r, ki, 1, j.p1, j.p2, j.p3) - i0;

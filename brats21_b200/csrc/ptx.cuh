@@ -40,28 +40,65 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// mbarrier.try_wait suspends the thread until the phase completes or a time limit elapses.  Without a hint the limit is
+// short: a waiting warp re-issues try_wait + branch every few tens of cycles (ncu: 40 % of all issued instructions of
+// conv_input_kernel were these loops), polling shared memory next to the tensor core's operand reads.  The waits
+// therefore pass the optional suspend-time hint: the warp sleeps until the barrier flips.  Same-box A/B on v2_tta8
+// (profiles/r02x_wait_hint_ab.md): 291.9 -> 285.7 ms, all of it in conv_slide_kernel (108 -> 98 ms: its issuer waits for
+// a weight tile every 9 MMAs); hinting only producers / epilogues gave nothing, and conv_march's scout — which waits
+// on barriers that have usually flipped already — is ~1 % faster with the plain spin (mbar_wait_spin_a).
+#ifndef B21_WAIT_HINT_NS
+#define B21_WAIT_HINT_NS 1000
+#endif
+constexpr uint32_t kWaitHintNs = B21_WAIT_HINT_NS;
+// Bounded wait: a mis-programmed pipeline traps instead of hanging the GPU box (a hang is a "strike").
+constexpr uint32_t kSpinLimit = 1u << 26;
+constexpr uint32_t kHintSpinLimit = kWaitHintNs ? (4000000000u / kWaitHintNs + 1024u) : kSpinLimit;
+__device__ __forceinline__ bool mbar_try_wait_spin_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a mis-programmed pipeline traps instead of hanging the GPU box (a hang is a "strike").
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("b21: mbarrier timeout block(%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
-  }
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  if constexpr (kWaitHintNs == 0) return mbar_try_wait_spin_a(bar, parity);
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(kWaitHintNs)
+      : "memory");
+  return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("b21: mbarrier timeout block(%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, bar,
+         parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity))
+    if (++spins > kHintSpinLimit) mbar_timeout(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+// plain spin (no suspend hint): for a thread whose barriers have usually flipped before it looks (conv_march's scout)
+__device__ __forceinline__ void mbar_wait_spin_a(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_spin_a(bar, parity))
+    if (++spins > kSpinLimit) mbar_timeout(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) { mbar_wait_spin_a(smem_u32(bar), parity); }
+// (kept as names of their own: the waits of producers / epilogue warps, which sleep most of the time)
+__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t bar, uint32_t parity) { mbar_wait_a(bar, parity); }
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // Same operations on a 32-bit shared-window address (avoids the generic->shared conversion on hot paths).
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
@@ -69,25 +106,6 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) {
-      printf("b21: mbarrier timeout block(%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
 }
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -154,6 +172,18 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA tile STORE shared -> global (bulk async-group completion); out-of-bounds elements of the box are not written.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // 1-D bulk copy global -> shared (no tensor map); size multiple of 16 B, both sides 16 B aligned.
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

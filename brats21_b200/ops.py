@@ -4,6 +4,8 @@ must be 1 and the voxel stride (`t.stride(3)`) is passed as the leading dimensio
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -78,6 +80,11 @@ class PackedConv:
         if k == 3 and self.w_march is None and lib.b21_conv_slide_supported(cin_padded, rows):
             nbytes = lib.b21_conv_slide_weight_bytes(cin_padded, rows)
             self.w_slide = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
+        # first-conv packing (k = 3, at most 4 real input channels): im2col plane blocks, see csrc/conv_input.cu
+        self.w_input = None
+        if k == 3 and not transpose_flip and lib.b21_conv_input_supported(inner, rows):
+            nbytes = lib.b21_conv_input_weight_bytes(rows)
+            self.w_input = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=weight.device)
         self._launch_packs()
 
     def _launch_packs(self):
@@ -88,6 +95,8 @@ class PackedConv:
             call("b21_pack_conv_weight_march", ptr(self.w32), ptr(self.w_march), cout, cin, tf, stream_ptr())
         if self.w_slide is not None:
             call("b21_pack_conv_weight_slide", ptr(self.w32), ptr(self.w_slide), cout, cin, tf, stream_ptr())
+        if self.w_input is not None:
+            call("b21_pack_conv_weight_input", ptr(self.w32), ptr(self.w_input), cout, cin, stream_ptr())
         if "ws" in self._fold:
             call("b21_border_weight_sums", ptr(self.w32), ptr(self._fold["ws"]), self.cout, self.cin_true, self.taps,
                  stream_ptr())
@@ -121,6 +130,8 @@ class PackedConv:
             add("b21_pack_job_march", ptr(self.w32), ptr(self.w_march), cout, cin, tf)
         if self.w_slide is not None:
             add("b21_pack_job_slide", ptr(self.w32), ptr(self.w_slide), cout, cin, tf)
+        if self.w_input is not None:
+            add("b21_pack_job_input", ptr(self.w32), ptr(self.w_input), cout, cin)
         return jobs
 
 
@@ -146,6 +157,10 @@ def conv3d(x: torch.Tensor, pw: PackedConv, out: torch.Tensor | None = None, sta
         kind = "point"
         call("b21_conv1x1_fwd", ptr(x), _ld(x), ptr(pw.w), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
              n, d * h * w, cin, pw.cout, stream_ptr())
+    elif use_input and dil == 1 and pw.w_input is not None and _ld(x) == 8:
+        kind = "input"
+        call("b21_conv3d_input_fwd", ptr(x), _ld(x), ptr(pw.w_input), ptr(pw.bias), ptr(out), _ld(out), ptr(stats), 0,
+             n, d, h, w, pw.cout, stream_ptr())
     elif use_march and dil == 1 and pw.w_march is not None and h >= 8 and w >= 8:
         kind = "march"
         call("b21_conv3d_march_fwd", ptr(x), _ld(x), ptr(pw.w_march), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
@@ -247,6 +262,10 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
         assert pw.point_ok and chan_sum is None
         call("b21_conv1x1_fwd_fold", ptr(x), _ld(x), ptr(wts), int(wstride != 0), ptr(pw.bias), ptr(table), ptr(out),
              _ld(out), ptr(stats), int(act), n, d * h * w, cin, pw.cout, stream_ptr())
+    elif use_input and pw.w_input is not None and ab is None and chan_sum is None and x2 is None and _ld(x) == 8:
+        act_code = (2 if fast_input_swish else 1) if act else 0
+        call("b21_conv3d_input_fwd", ptr(x), _ld(x), ptr(pw.w_input), ptr(pw.bias), ptr(out), _ld(out), ptr(stats),
+             act_code, n, d, h, w, pw.cout, stream_ptr())
     else:
         assert h >= 8 and w >= 8
         name = "b21_conv3d_march_fwd_fold" if pw.w_march is not None else "b21_conv3d_slide_fwd_fold"
@@ -263,6 +282,8 @@ def conv3d_fold(x, pw: "PackedConv", out, stats, ab=None, act=True, chan_sum=Non
     if prof is not None:
         e1.record()
         kind = "point" if pw.taps == 1 else ("march" if pw.w_march is not None else "slide")
+        if use_input and pw.w_input is not None and ab is None and chan_sum is None and x2 is None and _ld(x) == 8:
+            kind = "input"
         prof.append((e0, e1, 2.0 * n * d * h * w * pw.cin_true * pw.cout * pw.taps, (kind, cin, pw.cout, pw.taps, d)))
         if kind == "point" and hbm_profile is not None:
             hbm_profile.append((e0, e1, 2.0 * n * d * h * w * (cin + pw.cout), "conv1x1"))
@@ -284,6 +305,9 @@ def affine_pool(x, a_in, b_in, pooled, mode=2):
 conv_profile = None
 # The plane-marching kernel is the default for the shapes it supports; tools flip this to time the tap kernel.
 use_march = True
+# im2col first-conv kernel (conv_input.cu) for k = 3 convs with at most 4 real input channels; B21_INPUT_CONV=0 or tests
+# flip it back to the plane-marching kernel
+use_input = os.environ.get("B21_INPUT_CONV", "1") != "0"
 # sliding-window kernel (conv_slide.cu) for the k = 3 shapes whose weights do not fit the march kernel
 use_slide = True
 # folded-EvoNorm inference path of EquiUnetASSPEvo (csrc/fold.cu); tests flip it to compare both formulations

@@ -102,6 +102,21 @@ int b21_pack_job_march(const float* w, void* packed, int cout, int cin, int tran
 int b21_pack_job_slide(const float* w, void* packed, int cout, int cin, int transpose_flip, b21_pack_job* job);
 int b21_pack_batch(const b21_pack_job* jobs_dev, int njobs, int total_blocks, void* stream);
 
+/* First convolution of the networks (k = 3, dilation 1, at most 4 real input channels: networks/equiunet2020.py:19-25
+ * encoder1.ConvBnRelu1, networks/equiunet2021.py:198 encoder1.conv_evo_1).  With 8 bytes per voxel the plane-marching
+ * kernel is bound by its per-plane hand-shakes, so this variant builds the im2col of each input plane in shared memory
+ * (8-byte cp.async, zero fill = padding; k = (kh*3+kw)*4 + c, 36 -> 48), folds the three kd taps into N and groups the
+ * output planes in quads: 18 tcgen05.mma per four planes, every barrier / commit once per two or four planes.  x holds the real channels in the first
+ * 8 bytes of each dense 16-byte voxel record (ldx = 8); same bias / stats semantics as b21_conv3d_fwd;
+ * act: 0 none, 1 swish (x * sigmoid x) before the store, 2 the same through tanh.approx.  The weight is packed by
+ * b21_pack_conv_weight_input into b21_conv_input_weight_bytes(cout) bytes: bf16 [6][3*cout/8][8 n][8 k], n = (2-kd)*cout + co. */
+int b21_conv_input_supported(int cin_true, int cout);
+long long b21_conv_input_weight_bytes(int cout);
+int b21_pack_conv_weight_input(const float* w, void* packed, int cout, int cin, void* stream);
+int b21_pack_job_input(const float* w, void* packed, int cout, int cin, b21_pack_job* job);
+int b21_conv3d_input_fwd(const void* x, int ldx, const void* w_input, const float* bias, void* y, int ldy,
+                         double* stats, int act, int n, int d, int h, int w, int cout, void* stream);
+
 /* Persistent 1x1x1 variant of b21_conv3d_fwd (taps = 1) for the HBM-bound ConvEvo bridges / up-convs
  * (networks/equiunet2021.py:214-222,262-269): weights resident in shared memory, activation tiles streamed through a
  * TMA ring, double-buffered TMEM accumulator.  x / y are [n][nvox][ld] bf16; `w_packed` is the k = 1 packing of

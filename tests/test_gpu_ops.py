@@ -178,6 +178,53 @@ def test_conv_fold_matches_explicit_affine(cin, cout, k, shape):
     assert torch.equal(out2, ops.conv3d(s_in, pw))
 
 
+@pytest.mark.parametrize("cin,cout,shape", [
+    (4, 48, (2, 8, 16, 8)), (4, 48, (1, 5, 7, 9)), (4, 16, (3, 1, 8, 8)), (3, 32, (1, 2, 20, 13)),
+    (1, 64, (2, 11, 17, 24)),
+    # two items per CTA (256 tiles on 148 SMs), odd plane count: block-pair stages and accumulator buffers wrap many times
+    (4, 48, (4, 21, 128, 64)), (4, 48, (1, 128, 128, 128))])
+def test_conv_input_matches_torch_and_march(cin, cout, shape):
+    """First-conv kernel (csrc/conv_input.cu: im2col plane blocks built with cp.async, pairs of planes per hand-shake):
+    same result as F.conv3d on the bf16-rounded operands, statistics of the pre-activation, swish variants, and the
+    same values as the plane-marching kernel it replaces."""
+    from brats21_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(cin * 100 + cout + shape[1])
+    n, d, h, w = shape
+    x = torch.randn((n, cin, d, h, w), device=DEV, generator=g)
+    wt = torch.randn((cout, cin, 3, 3, 3), device=DEV, generator=g) / (cin * 27) ** 0.5
+    b = torch.randn((cout,), device=DEV, generator=g)
+    xb = torch.zeros((n, d, h, w, 8), device=DEV, dtype=torch.bfloat16)
+    xb[..., :cin] = _cl(x)
+    pw = ops.PackedConv(wt, b)
+    assert pw.w_input is not None and pw.cin == 8
+    ref = F.conv3d(xb[..., :cin].float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), b, padding=1)
+    saved = ops.use_input
+    try:
+        ops.use_input = True
+        st = ops.new_stats(n, DEV)
+        y = ops.conv3d(xb, pw, stats=st)
+        assert (_nc(y) - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+        r = ref.reshape(n, 8, cout // 8, -1).double()
+        sm = st.sum(0)
+        assert torch.allclose(sm[..., 0], r.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(sm[..., 1], (r * r).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+        sw = ref * torch.sigmoid(ref)
+        for fast in (False, True):
+            ops.fast_input_swish = fast
+            out = torch.empty_like(y)
+            st2 = ops.new_stats(n, DEV)
+            ops.conv3d_fold(xb, pw, out, st2, ab=None, act=True)
+            assert (_nc(out) - sw).abs().max().item() <= 2 ** -7 * sw.abs().max().item() + 2e-3
+            assert torch.allclose(st2.sum(0), sm, rtol=1e-6, atol=1e-6)
+        ops.use_input = False
+        if h >= 8 and w >= 8:
+            y_march = ops.conv3d(xb, pw)
+            assert (y.float() - y_march.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    finally:
+        ops.use_input = saved
+        ops.fast_input_swish = True
+
+
 def test_evo_se_affine_and_affine_pool():
     from brats21_b200 import ops
     from oracle import nets
