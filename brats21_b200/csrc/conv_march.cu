@@ -107,7 +107,7 @@ constexpr int kMsgRing = 8;
 template <int COUT, int NG, int KS>
 __global__ void __launch_bounds__(kMThreadsBase + NG * 128 + 32, 1)
 conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
-                  const ConvMarchParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const ConvMarchParams p) {
   constexpr int kMThreads = kMThreadsBase + NG * 128 + 32;  // + the scout warp
   constexpr int PC = NG > 2 ? 16 : COUT;  // columns per epilogue pass
   // Accumulator slots in TMEM: RING logical slots + 2 OVERFLOW slots.  The three column groups of a plane are adjacent
@@ -135,6 +135,9 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t w_addr = smem_u32(smem);
   const uint32_t p_addr = w_addr + ((p.wbytes + 127u) & ~127u);
   const uint32_t plane_bytes = uint32_t(p.kc) * kMChunkBytes;
+  // output staging of the TMA-store epilogue: one dense 32-voxel x COUT bf16 tile (4 h rows x 8 w) per epilogue warp
+  constexpr uint32_t kStageTile = 32 * COUT * 2;
+  const uint32_t y_addr = p_addr + uint32_t(p.stages) * plane_bytes;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   const uint32_t accf0 = smem_u32(&accf_bar[0]), acce0 = smem_u32(&acce_bar[0]);
 
@@ -151,6 +154,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmX2);
+    tma_prefetch_desc(&tmY);
   }
   if (threadIdx.x == 0) msg_ready = 0;
   if (threadIdx.x < NG * 32) s_stat[threadIdx.x >> 5][(threadIdx.x >> 4) & 1][threadIdx.x & 15] = 0.f;
@@ -391,6 +395,8 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     uint32_t r = 0, use_par = 0, plane_cnt = 0;
     int buf = 0;
+    const uint32_t y_tile = y_addr + uint32_t(warp - 2) * kStageTile;
+    uint8_t* y_row = smem + (y_tile - w_addr) + size_t(lane) * (COUT * 2);  // this thread's voxel record of the tile
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const MarchItem it = decode_item(p, item);
       const int h = it.h0 + hh, w = it.w0 + ww;
@@ -405,9 +411,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float* trow = p.ex.table
                               ? p.ex.table + (size_t(it.n) * 27 + border_class(h, p.H) * 3 + border_class(w, p.W)) * COUT
                               : nullptr;
-      __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy);
-      const size_t ystep = size_t(p.H) * p.W * p.ldy;
-      for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
+      for (int so = 0; so < it.Lc; ++so) {
         if (int((plane_cnt++) % uint32_t(NG)) != grp) {  // another group's plane: only advance the ring cursor
           use_par ^= 1u << r;
           r = r + 1 == RING ? 0 : r + 1;
@@ -416,6 +420,8 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait_sleep_a(accf0 + 8u * r, (use_par >> r) & 1u);
         use_par ^= 1u << r;
         tc_fence_after();
+        if (lane == 0) bulk_wait_read0();  // the previous TMA store of this warp has finished reading the staging tile
+        __syncwarp();
         const uint32_t tcol = tlane + r * COUT;
         const bool aliased = r < 2;  // logical slots 0 and 1 have a second physical copy (slots RING, RING + 1)
         const uint32_t tcol2 = tcol + RING * COUT;
@@ -485,10 +491,19 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             q.y = pack_bf16x2(v[c + 2], v[c + 3]);
             q.z = pack_bf16x2(v[c + 4], v[c + 5]);
             q.w = pack_bf16x2(v[c + 6], v[c + 7]);
-            if (valid && !(p.variant & 8)) *reinterpret_cast<uint4*>(yrow + c0 + c) = q;
+            *reinterpret_cast<uint4*>(y_row + (c0 + c) * 2) = q;
           }
         }
         if (p.variant & 32) continue;
+        // One TMA store per warp and plane (box {COUT, 8 w, 4 h}; rows / columns beyond H / W are clipped).  A
+        // thread-per-voxel st.global.v4 touches 24 lines per instruction: 576 LSU cycles per 48-channel plane on the
+        // L1 / shared-memory data path the tensor core reads its operands through (profiles/r02w_input_conv.md).
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(p.variant & 8)) {
+          tma_store_5d(&tmY, y_tile, 0, it.w0, it.h0 + quad * 4, it.d0 + so, it.n);
+          bulk_commit();
+        }
         if constexpr (PC == COUT) {
           if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
 #pragma unroll
@@ -537,6 +552,7 @@ conv_march_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         buf ^= 1;
       }
     }
+    if (lane == 0) bulk_wait0();  // the last TMA stores have completed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -566,11 +582,13 @@ __global__ void pack_march_weight_kernel(const float* __restrict__ w, __nv_bfloa
 static inline int march_kc(int cin) { return (cin + 15) / 16 * 2; }
 static inline size_t march_wbytes(int cin, int cout) { return size_t(9) * march_kc(cin) * (3 * cout / 8) * 128; }
 
+// output staging of the epilogue warps (TMA store): 16 warps cover the NG = 4 variant of the Cin = 8 layers
+static inline size_t march_staging(int cin, int cout) { return size_t(cin <= 8 ? 16 : 8) * 32 * cout * 2; }
 static int march_stages(int cin, int cout) {
   const size_t wb = (march_wbytes(cin, cout) + 127) & ~size_t(127);
   const size_t plane = size_t(march_kc(cin)) * kMChunkBytes;
-  if (wb + 128 >= size_t(kMSmemBudget)) return 0;
-  size_t st = (size_t(kMSmemBudget) - wb - 128) / plane;
+  if (wb + 128 + march_staging(cin, cout) >= size_t(kMSmemBudget)) return 0;
+  size_t st = (size_t(kMSmemBudget) - wb - 128 - march_staging(cin, cout)) / plane;
   return int(st > kMMaxStages ? kMMaxStages : st);
 }
 
@@ -626,30 +644,30 @@ extern "C" int b21_pack_conv_weight_march_fold(const float* w, void* packed, int
 }
 
 template <int COUT, int NG, int KS>
-static int launch_march_ng(const CUtensorMap& tm, const CUtensorMap& tm2, const ConvMarchParams& p, size_t smem_bytes,
-                           int grid, cudaStream_t stream) {
+static int launch_march_ng(const CUtensorMap& tm, const CUtensorMap& tm2, const CUtensorMap& tmY, const ConvMarchParams& p,
+                           size_t smem_bytes, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     B21_CUDA(cudaFuncSetAttribute(conv_march_kernel<COUT, NG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMSmemBudget));
     attr_set = true;
   }
-  conv_march_kernel<COUT, NG, KS><<<grid, kMThreadsBase + NG * 128 + 32, smem_bytes, stream>>>(tm, tm2, p);
+  conv_march_kernel<COUT, NG, KS><<<grid, kMThreadsBase + NG * 128 + 32, smem_bytes, stream>>>(tm, tm2, tmY, p);
   B21_LAUNCH_CHECK("conv_march_kernel");
   return B21_OK;
 }
 
 template <int COUT>
-static int launch_march(const CUtensorMap& tm, const CUtensorMap& tm2, const ConvMarchParams& p, size_t smem_bytes,
-                        int grid, cudaStream_t stream) {
+static int launch_march(const CUtensorMap& tm, const CUtensorMap& tm2, const CUtensorMap& tmY, const ConvMarchParams& p,
+                        size_t smem_bytes, int grid, cudaStream_t stream) {
   const int ks = (p.variant & 256) ? 0 : p.kc >> 1;
   // epilogue-bound input conv (one real 8-channel chunk, no SE channel sums): four epilogue groups
-  if (p.merged && !p.ex.chan_sum && !(p.variant & 128)) return launch_march_ng<COUT, 4, 1>(tm, tm2, p, smem_bytes, grid, stream);
+  if (p.merged && !p.ex.chan_sum && !(p.variant & 128)) return launch_march_ng<COUT, 4, 1>(tm, tm2, tmY, p, smem_bytes, grid, stream);
   switch (ks) {
-    case 1: return launch_march_ng<COUT, 2, 1>(tm, tm2, p, smem_bytes, grid, stream);
-    case 2: return launch_march_ng<COUT, 2, 2>(tm, tm2, p, smem_bytes, grid, stream);
-    case 3: return launch_march_ng<COUT, 2, 3>(tm, tm2, p, smem_bytes, grid, stream);
-    default: return launch_march_ng<COUT, 2, 0>(tm, tm2, p, smem_bytes, grid, stream);
+    case 1: return launch_march_ng<COUT, 2, 1>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    case 2: return launch_march_ng<COUT, 2, 2>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    case 3: return launch_march_ng<COUT, 2, 3>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    default: return launch_march_ng<COUT, 2, 0>(tm, tm2, tmY, p, smem_bytes, grid, stream);
   }
 }
 
@@ -778,11 +796,20 @@ static int march_fwd_impl(const void* x, int ldx, const void* w_march, const flo
     if (r) return r;
   }
   if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
-  const size_t smem_bytes = ((size_t(p.wbytes) + 127) & ~size_t(127)) + size_t(p.stages) * p.kc * kMChunkBytes + 128;
+  const size_t smem_bytes = ((size_t(p.wbytes) + 127) & ~size_t(127)) + size_t(p.stages) * p.kc * kMChunkBytes +
+                            march_staging(cin, cout) + 128;
+  CUtensorMap tmY;
+  {
+    const uint64_t dims[5] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t str[4] = {uint64_t(ldy) * 2, uint64_t(w) * ldy * 2, uint64_t(h) * w * ldy * 2, uint64_t(d) * h * w * ldy * 2};
+    const uint32_t box[5] = {(uint32_t)cout, (uint32_t)kMTW, 4, 1, 1};
+    int r = encode_tmap_bf16(&tmY, y, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
   switch (cout) {
-    case 16: return launch_march<16>(tm, tm2, p, smem_bytes, grid, stream);
-    case 32: return launch_march<32>(tm, tm2, p, smem_bytes, grid, stream);
-    case 48: return launch_march<48>(tm, tm2, p, smem_bytes, grid, stream);
-    default: return launch_march<64>(tm, tm2, p, smem_bytes, grid, stream);
+    case 16: return launch_march<16>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    case 32: return launch_march<32>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    case 48: return launch_march<48>(tm, tm2, tmY, p, smem_bytes, grid, stream);
+    default: return launch_march<64>(tm, tm2, tmY, p, smem_bytes, grid, stream);
   }
 }
