@@ -78,7 +78,7 @@ __device__ __forceinline__ SlideItem slide_decode(const ConvSlideParams& p, int 
 
 template <int NT, int GS, int KS0, int KS1>  // N tile, channels per norm group, k-steps of the two weight sub-stages
 __global__ void __launch_bounds__(kSThreads, 1)
-conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams p) {
+conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const ConvSlideParams p) {
   constexpr uint32_t RING = (512 / NT) < kSMaxRing ? (512 / NT) : kSMaxRing;  // accumulators in TMEM
   constexpr int NG = NT / GS;                                                 // norm groups covered by one N tile
   static_assert(NT % 16 == 0 && NT % GS == 0 && NG <= 8 && RING >= 4, "bad tile");
@@ -97,6 +97,11 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
   const uint32_t w_addr = smem_u32(smem);
   const uint32_t p_addr = w_addr + uint32_t(p.wstages) * p.wstage_bytes;
   const uint32_t plane_bytes = uint32_t(p.kc) * kSChunkBytes;
+  // output staging of the TMA-store epilogue: per epilogue warp one dense 32-voxel (4 h x 8 w) x SC-channel bf16 tile;
+  // a 96-channel tile goes out as two 48-channel halves through the same buffer
+  constexpr int SC = NT == 96 ? 48 : NT;
+  constexpr uint32_t kStageTile = 32 * SC * 2;
+  const uint32_t y_addr = p_addr + uint32_t(p.pslots) * plane_bytes;
   const uint32_t pfull0 = smem_u32(&pfull_bar[0]), pempty0 = smem_u32(&pempty_bar[0]);
   const uint32_t wfull0 = smem_u32(&wfull_bar[0]), wempty0 = smem_u32(&wempty_bar[0]);
   const uint32_t accf0 = smem_u32(&accf_bar[0]), acce0 = smem_u32(&acce_bar[0]);
@@ -116,6 +121,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
   }
   if (threadIdx.x < 32) s_stat[threadIdx.x >> 4][threadIdx.x & 15] = 0.f;
   if (warp == 1) {
@@ -344,6 +350,8 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
     const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
     uint32_t slot = 0, par = 0;
     int buf = 0;
+    const uint32_t y_tile = y_addr + uint32_t(quad) * kStageTile;
+    uint8_t* y_row = smem + (y_tile - w_addr) + size_t(lane) * (SC * 2);  // this thread's voxel record of the tile
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const SlideItem it = slide_decode(p, item);
       const int h = it.h0 + hh, w = it.w0 + ww;
@@ -352,8 +360,6 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       float gs[NG], gq[NG];
 #pragma unroll
       for (int g = 0; g < NG; ++g) gs[g] = gq[g] = 0.f;
-      __nv_bfloat16* yrow = p.y + (((size_t(it.n) * p.D + it.d0) * p.H + h) * p.W + w) * size_t(p.ldy) + cbase;
-      const size_t ystep = size_t(p.H) * p.W * p.ldy;
       const float* bias = p.bias ? p.bias + cbase : nullptr;
       const int cout_all = p.ntiles * NT;
       const float* trow = p.ex.table ? p.ex.table + (size_t(it.n) * 27 + border_class(h, p.H) * 3 + border_class(w, p.W)) *
@@ -363,7 +369,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
       float csum[NCS];  // lane l: running sum of the stored outputs of channels l, 32 + l, ...
 #pragma unroll
       for (int b = 0; b < NCS; ++b) csum[b] = 0.f;
-      for (int so = 0; so < it.Lc; ++so, yrow += ystep) {
+      for (int so = 0; so < it.Lc; ++so) {
         mbar_wait_sleep_a(accf0 + 8u * slot, par);
         tc_fence_after();
         float v[NT];
@@ -406,10 +412,24 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
         uint32_t o[NT / 2];
 #pragma unroll
         for (int c = 0; c < NT; c += 2) o[c / 2] = pack_bf16x2(v[c], v[c + 1]);
-        if (valid) {
+        // TMA store per warp, plane and SC-channel part (box {SC, 8 w, 4 h}; rows / columns beyond H / W are clipped): a
+        // thread-per-voxel st.global.v4 touches up to 32 lines per instruction on the L1 / shared-memory data path the
+        // tensor core reads its operands through (conv_march.cu, profiles/r02w_input_conv.md)
 #pragma unroll
-          for (int c0 = 0; c0 < NT; c0 += 8)
-            *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(o[c0 / 2], o[c0 / 2 + 1], o[c0 / 2 + 2], o[c0 / 2 + 3]);
+        for (int part = 0; part < NT / SC; ++part) {
+          if (lane == 0) bulk_wait_read0();  // the previous store of this warp has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 8) {
+            const int q = (part * SC + c0) / 2;
+            *reinterpret_cast<uint4*>(y_row + c0 * 2) = make_uint4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmY, y_tile, cbase + part * SC, it.w0, it.h0 + quad * 4, it.d0 + so, it.n);
+            bulk_commit();
+          }
         }
         if (p.ex.chan_sum) {  // SE squeeze: channel sums of what the consumer will read (the rounded values)
 #pragma unroll
@@ -454,6 +474,7 @@ conv_slide_kernel(const __grid_constant__ CUtensorMap tmX, const ConvSlideParams
         buf ^= 1;
       }
     }
+    if (lane == 0) bulk_wait0();  // the last TMA stores have completed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -507,20 +528,22 @@ static bool slide_config(int cin, int cout, SlideCfg* c) {
   // one chunk: 3 planes in use + 2 in flight; several chunks: a pass needs its third plane while the previous pass still
   // holds three, so one more slot keeps the pipeline full
   c->pslots = c->nchunks > 1 ? 6 : 5;
-  if (size_t(kSSmemBudget) < 128 + c->pslots * plane + 2 * size_t(c->wstage_bytes)) return false;
-  size_t ws = (size_t(kSSmemBudget) - 128 - c->pslots * plane) / c->wstage_bytes;
+  // output staging of the four epilogue warps (TMA store): 32 voxels x SC channels each, SC = 48 for the 96-wide tile
+  const size_t staging = size_t(4) * 32 * (c->nt == 96 ? 48 : c->nt) * 2;
+  if (size_t(kSSmemBudget) < 128 + staging + c->pslots * plane + 2 * size_t(c->wstage_bytes)) return false;
+  size_t ws = (size_t(kSSmemBudget) - 128 - staging - c->pslots * plane) / c->wstage_bytes;
   c->wstages = int(ws > size_t(kSMaxWStages) ? size_t(kSMaxWStages) : ws);
   if (c->wstages < (c->wsub == 2 ? 3 : 2)) return false;
   // spare room -> extra plane slots (deeper halo prefetch)
   while (c->pslots < kSMaxPSlots &&
-         128 + size_t(c->pslots + 1) * plane + size_t(c->wstages) * c->wstage_bytes <= size_t(kSSmemBudget))
+         128 + staging + size_t(c->pslots + 1) * plane + size_t(c->wstages) * c->wstage_bytes <= size_t(kSSmemBudget))
     ++c->pslots;
-  c->smem_bytes = 128 + size_t(c->pslots) * plane + size_t(c->wstages) * c->wstage_bytes;
+  c->smem_bytes = 128 + staging + size_t(c->pslots) * plane + size_t(c->wstages) * c->wstage_bytes;
   return true;
 }
 
 template <int NT, int GS, int KS0, int KS1>
-static int launch_slide(const CUtensorMap& tm, const ConvSlideParams& p, size_t smem_bytes, int grid,
+static int launch_slide(const CUtensorMap& tm, const CUtensorMap& tmY, const ConvSlideParams& p, size_t smem_bytes, int grid,
                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -528,7 +551,7 @@ static int launch_slide(const CUtensorMap& tm, const ConvSlideParams& p, size_t 
                                   kSSmemBudget));
     attr_set = true;
   }
-  conv_slide_kernel<NT, GS, KS0, KS1><<<grid, kSThreads, smem_bytes, stream>>>(tm, p);
+  conv_slide_kernel<NT, GS, KS0, KS1><<<grid, kSThreads, smem_bytes, stream>>>(tm, tmY, p);
   B21_LAUNCH_CHECK("conv_slide_kernel");
   return B21_OK;
 }
@@ -688,11 +711,19 @@ static int slide_fwd_impl(const void* x, int ldx, const void* w_slide, const flo
     int r = encode_tmap_bf16(&tm, x, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   }
+  CUtensorMap tmY;
+  {
+    const uint64_t dims[5] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)d, (uint64_t)n};
+    const uint64_t str[4] = {uint64_t(ldy) * 2, uint64_t(w) * ldy * 2, uint64_t(h) * w * ldy * 2, uint64_t(d) * h * w * ldy * 2};
+    const uint32_t box[5] = {(uint32_t)(c.nt == 96 ? 48 : c.nt), (uint32_t)kSTW, 4, 1, 1};
+    int r = encode_tmap_bf16(&tmY, y, 5, dims, str, box, (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
   if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
   const int gs = cout / 8, ks1 = c.ksteps - c.ks_sub;
 #define X(nt_, g_, k0, k1) \
   if (c.nt == nt_ && gs == g_ && c.ks_sub == k0 && ks1 == k1) \
-    return launch_slide<nt_, g_, k0, k1>(tm, p, c.smem_bytes, grid, stream);
+    return launch_slide<nt_, g_, k0, k1>(tm, tmY, p, c.smem_bytes, grid, stream);
   B21_SLIDE_SHAPES(X)
 #undef X
   set_error("conv3d_slide_fwd: shape not instantiated");
