@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 2200 -c 1600 --csv 
 python tools/summarize_ncu.py launches ${o}_launches.csv ${o}_launches_v2_tta8.md \
     "ncu launch list: 1600 consecutive launches (> one step) of python bench.py --steps 1 --warmup 1 --no-train" > /dev/null
 rm -f ${o}_launches.csv
-ncu --set full --clock-control none -k regex:"conv_slide|conv_march|conv_tap" -c 8 -f -o ${o}_conv \
+ncu --set full --clock-control none -k regex:"conv_input|conv_slide|conv_march|conv_tap" -c 9 -f -o ${o}_conv \
     python tools/layer_profile.py v2_tta8 > ${o}_conv.log 2>&1
 python tools/summarize_ncu.py full ${o}_conv.ncu-rep ${o}_conv_full.md "ncu --set full: first 8 conv launches of a v2_tta8 window batch (9 x 128^3)" > /dev/null
 ncu --set full --clock-control none -k regex:"conv_wgrad|norm_bwd_reduce|norm_bwd_apply" -c 8 -f -o ${o}_train \
