@@ -1,8 +1,10 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "Warning\|warnings.warn" | tail -60 > gpurun_out/r02aa_gputest.log; tail -2 gpurun_out/r02aa_gputest.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/r02aa_bench.json 2> gpurun_out/r02aa_bench.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02aa_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e'], d['roofline']['frac'], d.get('clocks'))
-t=d.get('train',{})
-print({k:t[k] for k in t if k in ('value','ms_per_step','e2e','conv_roofline_frac','conv_tflops')} or list(t.keys()))
-PY
+timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_networks.py -x -q 2>&1 | tail -3
+for i in 1 2; do
+for sw in 0 1; do
+  echo "== B21_UPSAMPLE_WIDE=$sw"
+  B21_UPSAMPLE_WIDE=$sw python bench.py --no-cpu-baseline --no-train --steps 5 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['hbm']['by_kernel']['upsample2x']
+print(d['ms_per_step'], round(r['ms'],2), round(r['gbs']), round(r['frac'],3))"
+done
+done
