@@ -58,7 +58,7 @@ struct ConvInputParams {
   int tilesH, tilesW, segs, L, items;
   int stages, act;
   uint32_t wbytes;
-  int variant;  // debug (B21_INPUT_VARIANT): 1 no global stores, 2 epilogue hand-shake only, 4 no MMAs, 8 no cp.async
+  int variant;  // debug (B21_INPUT_VARIANT): 1 no global stores, 2 epilogue hand-shake only, 4 no MMAs, 8 no TMA loads of the raw planes
 };
 
 struct InputItem {
