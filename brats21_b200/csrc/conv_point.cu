@@ -14,6 +14,10 @@
 //   * GroupNorm/EvoNorm group statistics are accumulated in registers across all tiles of a sample and flushed
 //     with one round of double atomics per CTA.
 //
+// Tile GROUPS (round 2): one 128-voxel tile per hand-shake made the kernel protocol-bound (two mbarrier waits and two
+// tcgen05.commit per 3-6 MMAs: 1520 cycles per tile against 755 of HBM time at 48 -> 24, 9 x 128^3).  A pipeline stage now
+// holds G = 4 (2 for Cout = 96) consecutive tiles of one sample, a TMEM buffer their G accumulators, and every barrier /
+// commit is per group.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 and 6..9 = two epilogue groups:
 // group g drains accumulator buffer g (tiles with it % 2 == g), so that one group's tcgen05.ld / MUFU / store
 // latency chain overlaps the other's (a single group left the SM idle for half of every tile: 1570 cycles per tile
@@ -27,7 +31,8 @@ namespace b21 {
 constexpr int kPtThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9: two epilogue groups (alternate tiles)
 constexpr int kPtABytes = 128 * 128;  // one stage: 128 voxels x 64 bf16
 constexpr int kPtMaxStages = 8;
-constexpr int kPtSmemBudget = 200 * 1024;
+constexpr int kPtSmemBudget = 225 * 1024;
+__host__ __device__ constexpr int point_group(int bn) { return bn <= 64 ? 4 : 2; }  // tiles per pipeline stage
 
 struct ConvPointParams {
   __nv_bfloat16* y;
@@ -45,7 +50,11 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const ConvPointParams p) {
   constexpr int BN = (COUT + 15) / 16 * 16;
   constexpr int GS = COUT / 8;
-  constexpr uint32_t TCOLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr int G = point_group(BN);
+  constexpr uint32_t kBufCols = G * BN;  // one TMEM buffer = the accumulators of a tile group
+  constexpr uint32_t TCOLS = 2 * kBufCols <= 32 ? 32 : (2 * kBufCols <= 64 ? 64 : (2 * kBufCols <= 128 ? 128 : (2 * kBufCols <= 256 ? 256 : 512)));
+  static_assert(2 * kBufCols <= 512, "accumulator buffers exceed TMEM");
+  constexpr uint32_t kStageBytes = G * kPtABytes;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPtMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kPtMaxStages];
@@ -58,7 +67,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                   // [chunks][BN rows][128 B]
-  uint8_t* sA = smem + size_t(p.chunks) * BN * 128;     // [stages][128 rows][128 B]
+  uint8_t* sA = smem + size_t(p.chunks) * BN * 128;     // [stages][G tiles][128 rows][128 B]
 
   // contiguous tile range of this CTA
   const int per = p.tiles / gridDim.x, rem = p.tiles % gridDim.x;
@@ -94,8 +103,11 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       int w_n = -1;
-      for (int tile = t_begin; tile < t_end; ++tile) {
+      for (int tile = t_begin; tile < t_end;) {
         const int n = tile / p.tiles_per_n;
+        int g = (n + 1) * p.tiles_per_n - tile;  // group: up to G consecutive tiles of one sample
+        g = g > G ? G : g;
+        g = g > t_end - tile ? t_end - tile : g;
         const int r0 = (tile - n * p.tiles_per_n) * 128;
         if (w_n < 0 || (p.ex.wstride != 0 && n != w_n)) {
           if (w_n >= 0) {  // every activation stage released <=> every MMA that read the old weights has completed
@@ -111,13 +123,15 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int ck = 0; ck < p.chunks; ++ck) {
           mbar_wait_sleep(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kPtABytes);
-          tma_load_3d(sA + size_t(s) * kPtABytes, &tmA, &full_bar[s], ck * 64, r0, n);
+          mbar_expect_tx(&full_bar[s], uint32_t(g) * kPtABytes);
+          for (int j = 0; j < g; ++j)
+            tma_load_3d(sA + size_t(s) * kStageBytes + size_t(j) * kPtABytes, &tmA, &full_bar[s], ck * 64, r0 + j * 128, n);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
+        tile += g;
       }
     }
   } else if (warp == 1) {
@@ -129,8 +143,11 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t it = 0;
       int w_n = -1;
       uint32_t w_par = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      for (int tile = t_begin; tile < t_end; ++it) {
         const int n = tile / p.tiles_per_n;
+        int g = (n + 1) * p.tiles_per_n - tile;
+        g = g > G ? G : g;
+        g = g > t_end - tile ? t_end - tile : g;
         if (w_n < 0 || (p.ex.wstride != 0 && n != w_n)) {
           w_n = n;
           mbar_wait(&w_bar, w_par);
@@ -138,20 +155,22 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
         }
         const uint32_t buf = it & 1u;
-        mbar_wait(&acce_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(&acce_bar[buf], ((it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t dcol = tmem_base + buf * BN;
+        const uint32_t dcol = tmem_base + buf * kBufCols;
         for (int ck = 0; ck < p.chunks; ++ck) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           int nk = (p.Cin - ck * 64 + 15) >> 4;
           nk = nk > 4 ? 4 : nk;
-          const uint32_t a0 = a_addr + uint32_t(s) * kPtABytes;
           const uint32_t b0 = b_addr + uint32_t(ck) * BN * 128;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = umma_smem_desc(a0 + k * 32, 16, 1024, kLayoutSw128);
-            const uint64_t bd = umma_smem_desc(b0 + k * 32, 16, 1024, kLayoutSw128);
-            umma_bf16(dcol, ad, bd, idesc, (ck | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < g; ++j) {
+            const uint32_t a0 = a_addr + uint32_t(s) * kStageBytes + uint32_t(j) * kPtABytes;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t ad = umma_smem_desc(a0 + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t bd = umma_smem_desc(b0 + k * 32, 16, 1024, kLayoutSw128);
+              umma_bf16(dcol + uint32_t(j) * BN, ad, bd, idesc, (ck | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
@@ -160,6 +179,7 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&accf_bar[buf]);
+        tile += g;
       }
     }
   } else {
@@ -186,11 +206,14 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     };
     uint32_t it = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-      if ((it & 1u) != grp) continue;  // the other group's tile (and accumulator buffer)
+    for (int tile = t_begin; tile < t_end; ++it) {
       const int n = tile / p.tiles_per_n;
-      const long long r = (long long)(tile - n * p.tiles_per_n) * 128 + row;
-      const bool valid = r < p.nvox;
+      int g = (n + 1) * p.tiles_per_n - tile;
+      g = g > G ? G : g;
+      g = g > t_end - tile ? t_end - tile : g;
+      const int tile0 = tile;
+      tile += g;
+      if ((it & 1u) != grp) continue;  // the other group's tiles (and accumulator buffer)
       if (n != cur_n) {
         flush(cur_n);
         cur_n = n;
@@ -198,36 +221,42 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t buf = it & 1u;
       mbar_wait_sleep(&accf_bar[buf], (it >> 1) & 1u);
       tc_fence_after();
-      float v[BN];
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 16) tmem_ld16(tlane + buf * BN + uint32_t(c0), v + c0);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acce_bar[buf]);
       const float* tb = p.ex.table ? p.ex.table + size_t(n) * COUT : nullptr;
+      for (int j = 0; j < g; ++j) {
+        const long long r = (long long)(tile0 + j - n * p.tiles_per_n) * 128 + row;
+        const bool valid = r < p.nvox;
+        float v[BN];
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) {
-        const float val = v[c] + (tb ? __ldg(tb + c) : s_bias[c]);
-        const float sv = valid ? val : 0.f;
-        gs[c / GS] += sv;
-        gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
-        v[c] = val;
-      }
-      if (p.ex.act) {  // one branch around the whole unrolled loop: the ex2/rcp chains interleave
+        for (int c0 = 0; c0 < BN; c0 += 16) tmem_ld16(tlane + buf * kBufCols + uint32_t(j * BN + c0), v + c0);
+        tmem_ld_wait();
+        if (j == g - 1) {  // the whole buffer is in registers: the issuer may start the next group here
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acce_bar[buf]);
+        }
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) v[c] = swishf(v[c]);
-      }
-      if (valid) {
-        __nv_bfloat16* yrow = p.y + (size_t(n) * p.nvox + r) * size_t(p.ldy);
+        for (int c = 0; c < COUT; ++c) {
+          const float val = v[c] + (tb ? __ldg(tb + c) : s_bias[c]);
+          const float sv = valid ? val : 0.f;
+          gs[c / GS] += sv;
+          gq[c / GS] = fmaf(sv, sv, gq[c / GS]);
+          v[c] = val;
+        }
+        if (p.ex.act) {  // one branch around the whole unrolled loop: the ex2/rcp chains interleave
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 8) {
-          uint4 o;
-          o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
-          o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
-          o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
-          o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
-          *reinterpret_cast<uint4*>(yrow + c0) = o;
+          for (int c = 0; c < COUT; ++c) v[c] = swishf(v[c]);
+        }
+        if (valid) {
+          __nv_bfloat16* yrow = p.y + (size_t(n) * p.nvox + r) * size_t(p.ldy);
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[c0 + 0], v[c0 + 1]);
+            o.y = pack_bf16x2(v[c0 + 2], v[c0 + 3]);
+            o.z = pack_bf16x2(v[c0 + 4], v[c0 + 5]);
+            o.w = pack_bf16x2(v[c0 + 6], v[c0 + 7]);
+            *reinterpret_cast<uint4*>(yrow + c0) = o;
+          }
         }
       }
     }
@@ -241,8 +270,9 @@ conv_point_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 static inline int point_bn(int cout) { return (cout + 15) / 16 * 16; }
 static inline int point_stages(int cin, int cout) {
   const size_t wb = size_t((cin + 63) / 64) * point_bn(cout) * 128;
-  if (wb + 1024 + 2 * kPtABytes > size_t(kPtSmemBudget)) return 0;
-  size_t st = (size_t(kPtSmemBudget) - 1024 - wb) / kPtABytes;
+  const size_t stage = size_t(point_group(point_bn(cout))) * kPtABytes;
+  if (wb + 1024 + 2 * stage > size_t(kPtSmemBudget)) return 0;
+  size_t st = (size_t(kPtSmemBudget) - 1024 - wb) / stage;
   return int(st > kPtMaxStages ? kPtMaxStages : st);
 }
 
@@ -267,7 +297,7 @@ using namespace b21;
 extern "C" int b21_conv_point_supported(int cin, int cout) {
   if (!(cout == 8 || cout == 16 || cout == 24 || cout == 32 || cout == 48 || cout == 64 || cout == 96)) return 0;
   if (cin <= 0 || cin % 8) return 0;
-  return point_stages(cin, cout) >= 3 ? 1 : 0;
+  return point_stages(cin, cout) >= 2 ? 1 : 0;
 }
 
 static int point_fwd_impl(const void* x, int ldx, const void* w_packed, const float* bias, void* y, int ldy,
@@ -329,7 +359,7 @@ static int point_fwd_impl(const void* x, int ldx, const void* w_packed, const fl
   if (stats) B21_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * B21_STAT_SLOTS * n * 16, stream));
   const int sms = num_sms();
   const int grid = p.tiles < sms ? p.tiles : sms;
-  const size_t smem_bytes = size_t(p.chunks) * bn * 128 + size_t(p.stages) * kPtABytes + 1024;
+  const size_t smem_bytes = size_t(p.chunks) * bn * 128 + size_t(p.stages) * point_group(bn) * kPtABytes + 1024;
   switch (cout) {
     case 8: return launch_point<8>(tmA, tmB, p, smem_bytes, grid, stream);
     case 16: return launch_point<16>(tmA, tmB, p, smem_bytes, grid, stream);
